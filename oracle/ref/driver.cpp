@@ -285,7 +285,7 @@ static void dump_state(const std::string& dir, Opt* opt, DotOpt* dot, long heCap
 static void usage()
 {
     std::cerr << "dot_ref --script <file.txt> [--mesh <file.msh>] [--energy SNH|FCR] [--parts K] [--stepper DOT|Newton]\n"
-                 "        [--tol T] [--dt DT] [--anim <script name>] [--frames N] [--threads N] [--quiet]\n"
+                 "        [--tol T] [--dt DT] [--anim <script name>] [--frames N] [--threads N] [--quiet] [--labels-only]\n"
                  "        [--dump-dir D] [--dump-frames a,b,c] [--he-cap N] [--kernel-state V.npy] [--stats-json file]\n";
 }
 
@@ -295,7 +295,7 @@ int main(int argc, char** argv)
     int parts = -1, frames = 10, threads = 0;
     long heCap = -1;
     double tol = -1, dtOverride = -1;
-    bool quiet = false;
+    bool quiet = false, labelsOnly = false;
     std::set<int> dumpFrames;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -311,6 +311,7 @@ int main(int argc, char** argv)
         else if (a == "--frames") frames = std::stoi(next());
         else if (a == "--threads") threads = std::stoi(next());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--labels-only") labelsOnly = true;
         else if (a == "--dump-dir") dumpDir = next();
         else if (a == "--he-cap") heCap = std::stol(next());
         else if (a == "--kernel-state") kernelState = next();
@@ -373,6 +374,17 @@ int main(int argc, char** argv)
         V_surf.resize(sVI, 3);
         F_surf.resize(SF.rows(), 3);
         for (int tI = 0; tI < SF.rows(); ++tI) for (int c = 0; c < 3; ++c) F_surf(tI, c) = tetIndToSurf[SF(tI, c)];
+    }
+    if (labelsOnly) {
+        // METIS labels exactly as ADMMDDTimeStepper's ctor obtains them (ADMMDDTimeStepper.cpp:88-92):
+        // k-way partition of the dual graph with the option vector of METIS.hpp:265-321.
+        DOT::METIS<DIM> partitions(*temp);
+        partitions.partMesh(config.partitionAmt);
+        std::vector<long long> ep(partitions.epart.begin(), partitions.epart.end());
+        mkdir(dumpDir.c_str(), 0777);
+        mkdir((dumpDir + "/setup").c_str(), 0777);
+        npy_i64(dumpDir + "/setup/epart.npy", {(long)ep.size()}, ep.data());
+        return 0;
     }
     {   // initSIMD (main.cpp:521-597)
         size_t size = std::ceil(temp->F.rows() / 4.f) * 4;
