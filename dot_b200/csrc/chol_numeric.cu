@@ -1,0 +1,648 @@
+// Numeric multifrontal Cholesky + solves, batched over many matrices, level-scheduled.
+//
+// Storage per supernode s (front size m, ns pivot columns, nb = m - ns):
+//   panel  L[panel + r*ns + c]     r in [0,m), c in [0,ns)   row-major; rows < ns hold the lower-triangular
+//                                   diagonal block L_ss, rows >= ns hold L_below
+//   cb     CB[cb + i*nb + j]       contribution block (lower triangle used), nb x nb row-major
+//   tinv   tinv[tinv + kb*64*64..] inverse of every 64x64 diagonal tile of L_ss (row-major, upper part zero)
+// Factorisation of one level: extend-add children CBs -> for every pivot tile kb: potrf(tile) + tile
+// inverse, trsm of the rows below (a GEMM with the tile inverse), rank-64 update of the whole trailing
+// front (rest of the panel + CB).  GEMM tiles are 64x64 per CTA on DMMA (mma.sync m8n8k4 f64).
+// Solves: per level fwd_top (block forward substitution with the tile inverses), fwd_below (update
+// vectors, gathered deterministically by the parent), and the mirror image going down.
+#include <algorithm>
+
+#include "chol_numeric.h"
+
+namespace dotgpu {
+
+namespace {
+
+constexpr int NB = CH_NB;
+constexpr int SLD = 36;  // smem leading dimension of a 64 x 32 operand chunk (conflict-free DMMA fragment loads)
+constexpr int KC = 32;
+
+struct Task2 { int s, a; };
+struct Task3 { int s; short a, b; };
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// sX[r][k] = (r < nrows && k < kw) ? src[(r)*ld + k] : 0   for r < 64, k < KC;  128 threads
+__device__ __forceinline__ void load_chunk(double* sX, const double* __restrict__ src, long long ld, int nrows, int kw) {
+    const int k = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int r = r0 + 4 * i;
+        double v = 0.0;
+        if (r < nrows && k < kw) v = src[(long long)r * ld + k];
+        sX[r * SLD + k] = v;
+    }
+}
+
+// acc += A_chunk * B_chunk^T ; warp (wr,wc) owns the 32x32 sub-tile
+__device__ __forceinline__ void mma_chunk(double (&acc)[4][4][2], const double* sA, const double* sB, int wr, int wc, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int k0 = 0; k0 < KC; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[(wr * 32 + i * 8 + g) * SLD + k0 + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = sB[(wc * 32 + j * 8 + g) * SLD + k0 + q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+__global__ void k_scatter_a(long long nnz, const long long* __restrict__ amap, const double* __restrict__ a, double* __restrict__ L) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) L[amap[i]] = a[i];
+}
+
+// ---- extend-add: parent-driven, one CTA per (parent, 64-row slab), children processed in order ----
+__global__ void __launch_bounds__(256) k_extend_add(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                    const int* __restrict__ rel, const int* __restrict__ child,
+                                                    double* __restrict__ L, double* __restrict__ CB) {
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc p = sn[tk.s];
+    const int lo = tk.a * 64, hi = min(lo + 64, p.m);
+    const int nbp = p.m - p.ns;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int s_rng[2];
+    for (int ci = p.child_begin; ci < p.child_end; ++ci) {
+        const SNDesc c = sn[child[ci]];
+        const int nbc = c.m - c.ns;
+        const int* __restrict__ crel = rel + c.rows + c.ns;  // [nbc], ascending
+        if (threadIdx.x == 0) {
+            int a = 0, b = nbc;  // first i with crel[i] >= lo
+            while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < lo) a = mid + 1; else b = mid; }
+            s_rng[0] = a;
+            b = nbc;             // first i with crel[i] >= hi
+            while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < hi) a = mid + 1; else b = mid; }
+            s_rng[1] = a;
+        }
+        __syncthreads();
+        const int i0 = s_rng[0], i1 = s_rng[1];
+        const double* __restrict__ ccb = CB + c.cb;
+        for (int i = i0 + warp; i < i1; i += 8) {
+            const int r = crel[i];
+            for (int j = lane; j <= i; j += 32) {
+                const int cc = crel[j];
+                double v = ccb[(long long)i * nbc + j];
+                if (cc < p.ns) L[p.panel + (long long)r * p.ns + cc] += v;
+                else CB[p.cb + (long long)(r - p.ns) * nbp + (cc - p.ns)] += v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- potrf of pivot tile kb (+ its inverse), one CTA per supernode ----
+// C[n x n] (ld 65 or 33) = sign * A * B for n in {16,32}, operands in shared memory, 256 threads
+template <int N, int LDC>
+__device__ __forceinline__ void smem_gemm(double* C, const double* A, int lda, const double* B, int ldb, double sign) {
+    for (int e = threadIdx.x; e < N * N; e += 256) {
+        const int i = e / N, j = e % N;
+        double sum = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < N; ++k) sum += A[i * lda + k] * B[k * ldb + j];
+        C[i * LDC + j] = sign * sum;
+    }
+}
+
+constexpr int POTRF_SMEM = (2 * 64 * 65 + 32 * 33) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, int kb, const SNDesc* __restrict__ sn,
+                                               double* __restrict__ L, double* __restrict__ tinv, int* __restrict__ status) {
+    extern __shared__ double smem[];
+    double* T = smem;                  // [64][65] tile, then its Cholesky factor
+    double* X = smem + 64 * 65;        // [64][65] inverse of the factor
+    double* W = smem + 2 * 64 * 65;    // [32][33] scratch
+    const int s = tasks[blockIdx.x];
+    const SNDesc d = sn[s];
+    const int c0 = kb * NB;
+    const int w = min(NB, d.ns - c0);
+    double* __restrict__ tile = L + d.panel + (long long)c0 * d.ns + c0;
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        double v = 0.0;
+        if (r < w && c <= r) v = tile[(long long)r * d.ns + c];
+        else if (r >= w && c == r) v = 1.0;  // identity padding keeps the blocked inverse well defined
+        T[r * 65 + c] = v;
+        X[r * 65 + c] = 0.0;
+    }
+    __syncthreads();
+    const int ti = threadIdx.x >> 4, tk = threadIdx.x & 15;
+    for (int j = 0; j < w; ++j) {
+        if (threadIdx.x == 0) {
+            double a = T[j * 65 + j];
+            if (!(a > 0.0)) { atomicCAS(status, 0, s + 1); a = 1.0; }
+            T[j * 65 + j] = sqrt(a);
+        }
+        __syncthreads();
+        const double inv = 1.0 / T[j * 65 + j];
+        for (int i = j + 1 + threadIdx.x; i < w; i += 256) T[i * 65 + j] *= inv;
+        __syncthreads();
+        for (int i = j + 1 + ti; i < w; i += 16) {
+            const double lij = T[i * 65 + j];
+            for (int k = j + 1 + tk; k <= i; k += 16) T[i * 65 + k] -= lij * T[k * 65 + j];
+        }
+        __syncthreads();
+    }
+    // blocked inverse: four 16x16 diagonal blocks by forward substitution (one thread per column) ...
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x, b0 = c & ~15;
+        X[c * 65 + c] = 1.0 / T[c * 65 + c];
+        for (int i = c + 1; i < b0 + 16; ++i) {
+            double sum = 0.0;
+            for (int k = c; k < i; ++k) sum += T[i * 65 + k] * X[k * 65 + c];
+            X[i * 65 + c] = -sum / T[i * 65 + i];
+        }
+    }
+    __syncthreads();
+    // ... then inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1] at 32 and at 64
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int o = 32 * p;
+        smem_gemm<16, 33>(W, T + (o + 16) * 65 + o, 65, X + o * 65 + o, 65, 1.0);
+        __syncthreads();
+        smem_gemm<16, 65>(X + (o + 16) * 65 + o, X + (o + 16) * 65 + (o + 16), 65, W, 33, -1.0);
+        __syncthreads();
+    }
+    smem_gemm<32, 33>(W, T + 32 * 65, 65, X, 65, 1.0);
+    __syncthreads();
+    smem_gemm<32, 65>(X + 32 * 65, X + 32 * 65 + 32, 65, W, 33, -1.0);
+    __syncthreads();
+    double* __restrict__ tinvp = tinv + d.tinv + (long long)kb * NB * NB;
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        const bool in = (r < w && c <= r);
+        if (in) tile[(long long)r * d.ns + c] = T[r * 65 + c];
+        tinvp[e] = in ? X[r * 65 + c] : 0.0;
+    }
+}
+
+// ---- trsm: rows below pivot tile kb get multiplied by the tile inverse (transposed) ----
+__global__ void __launch_bounds__(128) k_trsm(const Task2* __restrict__ tasks, int kb, const SNDesc* __restrict__ sn,
+                                              double* __restrict__ L, const double* __restrict__ tinv) {
+    __shared__ double sA[64 * SLD], sB[64 * SLD];
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int c0 = kb * NB;
+    const int w = min(NB, d.ns - c0);
+    const int r0 = c0 + w + tk.a * 64;  // first row of this slab (w < NB only for the last pivot tile, where c0 + w == ns)
+    const int nrows = min(64, d.m - r0);
+    double* __restrict__ A = L + d.panel + (long long)r0 * d.ns + c0;
+    const double* __restrict__ B = tinv + d.tinv + (long long)kb * NB * NB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < w; k0 += KC) {
+        __syncthreads();
+        load_chunk(sA, A + k0, d.ns, nrows, w - k0);
+        load_chunk(sB, B + k0, NB, w, w - k0);
+        __syncthreads();
+        mma_chunk(acc, sA, sB, wr, wc, lane);
+    }
+    __syncthreads();  // all reads of A done before anybody overwrites it
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int r = wr * 32 + i * 8 + g, c = wc * 32 + j * 8 + 2 * q + e;
+                if (r < nrows && c < w) A[(long long)r * d.ns + c] = acc[i][j][e];
+            }
+}
+
+// ---- rank-w update of the trailing front with pivot block column kb ----
+__global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks, int kb, const SNDesc* __restrict__ sn,
+                                                double* __restrict__ L, double* __restrict__ CB) {
+    __shared__ double sA[64 * SLD], sB[64 * SLD];
+    const Task3 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int c0 = kb * NB;
+    const int w = min(NB, d.ns - c0);
+    const int base = c0 + w;
+    const int r0 = base + tk.a * 64, q0 = base + tk.b * 64;  // front-space origin of the C tile (rows r0.., cols q0..)
+    const int nrows = min(64, d.m - r0), ncols = min(64, d.m - q0);
+    const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns + c0;
+    const double* __restrict__ B = L + d.panel + (long long)q0 * d.ns + c0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < w; k0 += KC) {
+        __syncthreads();
+        load_chunk(sA, A + k0, d.ns, nrows, w - k0);
+        load_chunk(sB, B + k0, d.ns, ncols, w - k0);
+        __syncthreads();
+        mma_chunk(acc, sA, sB, wr, wc, lane);
+    }
+    const int g = lane >> 2, q = lane & 3;
+    const int nb = d.m - d.ns;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int rr = wr * 32 + i * 8 + g, cc = wc * 32 + j * 8 + 2 * q + e;
+                if (rr < nrows && cc < ncols) {
+                    int r = r0 + rr, c = q0 + cc;
+                    if (r >= c) {
+                        double* p = (c < d.ns) ? (L + d.panel + (long long)r * d.ns + c)
+                                               : (CB + d.cb + (long long)(r - d.ns) * nb + (c - d.ns));
+                        *p -= acc[i][j][e];
+                    }
+                }
+            }
+}
+
+// ---- forward solve, top part: y_s = L_ss^-1 (b_s + children updates) ----
+__global__ void __launch_bounds__(256) k_fwd_top(const int* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                 const long long* __restrict__ ea_ptr, const long long* __restrict__ ea_src,
+                                                 const double* __restrict__ L, const double* __restrict__ tinv,
+                                                 const double* __restrict__ b, const double* __restrict__ uwork,
+                                                 double* __restrict__ y) {
+    extern __shared__ double smem[];
+    const SNDesc d = sn[tasks[blockIdx.x]];
+    double* t = smem;            // [ns]
+    double* tmp = smem + d.ns;   // [64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < d.ns; k += 256) {
+        double v = b[d.col0 + k];
+        for (long long e = ea_ptr[d.rows + k]; e < ea_ptr[d.rows + k + 1]; ++e) v += uwork[ea_src[e]];
+        t[k] = v;
+    }
+    __syncthreads();
+    const double* __restrict__ P = L + d.panel;
+    for (int c0 = 0; c0 < d.ns; c0 += NB) {
+        const int w = min(NB, d.ns - c0);
+        // tmp[r] = t[c0+r] - L[c0+r, 0:c0] . x[0:c0]     (x overwrites t)
+        for (int r = warp; r < w; r += 8) {
+            const double* __restrict__ row = P + (long long)(c0 + r) * d.ns;
+            double sum = 0.0;
+            for (int k = lane; k < c0; k += 32) sum += row[k] * t[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+            if (lane == 0) tmp[r] = t[c0 + r] - sum;
+        }
+        __syncthreads();
+        const double* __restrict__ D = tinv + d.tinv + (long long)(c0 / NB) * NB * NB;
+        for (int r = warp; r < w; r += 8) {
+            double sum = 0.0;
+            for (int k = lane; k <= r; k += 32) sum += D[r * NB + k] * tmp[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+            if (lane == 0) t[c0 + r] = sum;
+        }
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < d.ns; k += 256) y[d.col0 + k] = t[k];
+}
+
+// ---- forward solve, below part: u_s = (children updates) - L_below y_s ----
+__global__ void __launch_bounds__(256) k_fwd_below(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                   const long long* __restrict__ ea_ptr, const long long* __restrict__ ea_src,
+                                                   const double* __restrict__ L, const double* __restrict__ y,
+                                                   double* __restrict__ uwork) {
+    extern __shared__ double smem[];
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < d.ns; k += 256) smem[k] = y[d.col0 + k];
+    __syncthreads();
+    const int nb = d.m - d.ns;
+    const int i0 = tk.a * 64, i1 = min(i0 + 64, nb);
+    for (int i = i0 + warp; i < i1; i += 8) {
+        const double* __restrict__ row = L + d.panel + (long long)(d.ns + i) * d.ns;
+        double sum = 0.0;
+        for (int k = lane; k < d.ns; k += 32) sum += row[k] * smem[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            double v = 0.0;
+            const long long gr = d.rows + d.ns + i;
+            for (long long e = ea_ptr[gr]; e < ea_ptr[gr + 1]; ++e) v += uwork[ea_src[e]];
+            uwork[d.u + i] = v - sum;
+        }
+    }
+}
+
+// ---- backward solve, below part: r_s[c] = sum_i L_below[i][c] x[rows_below[i]]  (64-column slab per CTA) ----
+__global__ void __launch_bounds__(256) k_bwd_below(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                   const int* __restrict__ rows, const double* __restrict__ L,
+                                                   const double* __restrict__ x, double* __restrict__ rwork) {
+    __shared__ double red[4][64];
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int c = tk.a * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
+    const int nb = d.m - d.ns;
+    double sum = 0.0;
+    if (c < d.ns) {
+        const int* __restrict__ rb = rows + d.rows + d.ns;
+        const double* __restrict__ P = L + d.panel + (long long)d.ns * d.ns + c;
+        for (int i = grp; i < nb; i += 4) sum += P[(long long)i * d.ns] * x[rb[i]];
+    }
+    red[grp][threadIdx.x & 63] = sum;
+    __syncthreads();
+    if (grp == 0 && c < d.ns) rwork[d.col0 + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// ---- backward solve, top part: x_s = L_ss^-T (y_s - r_s) ----
+__global__ void __launch_bounds__(256) k_bwd_top(const int* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                 const double* __restrict__ L, const double* __restrict__ tinv,
+                                                 const double* __restrict__ y, const double* __restrict__ rwork,
+                                                 double* __restrict__ x) {
+    extern __shared__ double smem[];
+    __shared__ double red[4][64];
+    const SNDesc d = sn[tasks[blockIdx.x]];
+    double* z = smem;           // [ns] -> solution
+    double* tmp = smem + d.ns;  // [64]
+    const bool has_below = d.m > d.ns;
+    for (int k = threadIdx.x; k < d.ns; k += 256) z[k] = y[d.col0 + k] - (has_below ? rwork[d.col0 + k] : 0.0);
+    __syncthreads();
+    const double* __restrict__ P = L + d.panel;
+    const int nblk = (d.ns + NB - 1) / NB;
+    const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        const int c0 = jb * NB;
+        const int w = min(NB, d.ns - c0);
+        // tmp[c] = z[c0+c] - sum_{k >= c0+w} L[k][c0+c] x[k]
+        double sum = 0.0;
+        if (cl < w) {
+            const double* __restrict__ col = P + c0 + cl;
+            for (int k = c0 + w + grp; k < d.ns; k += 4) sum += col[(long long)k * d.ns] * z[k];
+        }
+        red[grp][cl] = sum;
+        __syncthreads();
+        if (grp == 0 && cl < w) tmp[cl] = z[c0 + cl] - ((red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]));
+        __syncthreads();
+        // x[c] = sum_{k >= c} D[k][c] tmp[k]
+        const double* __restrict__ D = tinv + d.tinv + (long long)jb * NB * NB;
+        sum = 0.0;
+        if (cl < w)
+            for (int k = cl + grp; k < w; k += 4) sum += D[k * NB + cl] * tmp[k];
+        __syncthreads();
+        red[grp][cl] = sum;
+        __syncthreads();
+        if (grp == 0 && cl < w) z[c0 + cl] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < d.ns; k += 256) x[d.col0 + k] = z[k];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector<const int32_t*>& ja, const std::vector<int>& n,
+                        int leaf_nodes, cudaStream_t st) {
+    nmat = (int)n.size();
+    sym.assign(nmat, Symbolic());
+#pragma omp parallel for schedule(dynamic)
+    for (int m = 0; m < nmat; ++m) sym[m].analyze(n[m], ia[m], ja[m], leaf_nodes);
+    col_off.assign(nmat + 1, 0);
+    nnz_off.assign(nmat + 1, 0);
+    sn_off.assign(nmat + 1, 0);
+    std::vector<int64_t> panel_base(nmat + 1, 0), cb_base(nmat + 1, 0), u_base(nmat + 1, 0), rows_base(nmat + 1, 0),
+        ea_base(nmat + 1, 0), child_base(nmat + 1, 0);
+    nlevels = 0;
+    flops_total = 0.0;
+    for (int m = 0; m < nmat; ++m) {
+        const Symbolic& S = sym[m];
+        col_off[m + 1] = col_off[m] + S.n;
+        nnz_off[m + 1] = nnz_off[m] + (int64_t)S.amap.size();
+        sn_off[m + 1] = sn_off[m] + S.nsuper;
+        panel_base[m + 1] = panel_base[m] + S.nnz_l;
+        cb_base[m + 1] = cb_base[m] + S.cb_off[S.nsuper];
+        u_base[m + 1] = u_base[m] + S.u_off[S.nsuper];
+        rows_base[m + 1] = rows_base[m] + S.row_ptr[S.nsuper];
+        ea_base[m + 1] = ea_base[m] + (int64_t)S.ea_src.size();
+        child_base[m + 1] = child_base[m] + (int64_t)S.child_list.size();
+        nlevels = std::max(nlevels, S.nlevels);
+        flops_total += S.flops;
+    }
+    n_total = col_off[nmat];
+    nnz_a_total = nnz_off[nmat];
+    nnz_l_total = panel_base[nmat];
+    cb_total = cb_base[nmat];
+    u_total = u_base[nmat];
+    nsuper_total = sn_off[nmat];
+    DG_REQUIRE(n_total < (1LL << 31) && rows_base[nmat] < (1LL << 40), "batch too large");
+
+    std::vector<SNDesc> sn(nsuper_total);
+    std::vector<int> rows(rows_base[nmat]), rel(rows_base[nmat]), child(child_base[nmat]);
+    std::vector<long long> amap(nnz_a_total), ea_ptr(rows_base[nmat] + 1), ea_src(ea_base[nmat]);
+    tinv_total = 0;
+    for (int m = 0; m < nmat; ++m) {
+        const Symbolic& S = sym[m];
+        for (int s = 0; s < S.nsuper; ++s) {
+            SNDesc& d = sn[sn_off[m] + s];
+            d.panel = panel_base[m] + S.panel_off[s];
+            d.cb = cb_base[m] + S.cb_off[s];
+            d.u = u_base[m] + S.u_off[s];
+            d.rows = rows_base[m] + S.row_ptr[s];
+            d.m = S.front(s);
+            d.ns = S.nscol(s);
+            d.col0 = (int)(col_off[m] + S.super_ptr[s]);
+            d.child_begin = (int)(child_base[m] + S.child_ptr[s]);
+            d.child_end = (int)(child_base[m] + S.child_ptr[s + 1]);
+            d.parent = S.parent[s] < 0 ? -1 : sn_off[m] + S.parent[s];
+            d.tinv = tinv_total;
+            tinv_total += (int64_t)((d.ns + NB - 1) / NB) * NB * NB;
+        }
+        for (int64_t i = 0; i < S.row_ptr[S.nsuper]; ++i) {
+            rows[rows_base[m] + i] = (int)(col_off[m] + S.rows[i]);
+            rel[rows_base[m] + i] = S.rel[i];
+            ea_ptr[rows_base[m] + i] = ea_base[m] + S.ea_ptr[i];
+        }
+        for (size_t i = 0; i < S.ea_src.size(); ++i) ea_src[ea_base[m] + i] = u_base[m] + S.ea_src[i];
+        for (size_t i = 0; i < S.child_list.size(); ++i) child[child_base[m] + i] = sn_off[m] + S.child_list[i];
+        for (size_t i = 0; i < S.amap.size(); ++i) amap[nnz_off[m] + i] = panel_base[m] + S.amap[i];
+    }
+    ea_ptr[rows_base[nmat]] = ea_base[nmat];
+
+    // ---- level plans (levels merged across matrices) ----
+    plan.assign(nlevels, LevelPlan());
+    std::vector<int> tasks;
+    auto push2 = [&](int s, int a) { tasks.push_back(s); tasks.push_back(a); };
+    for (int lv = 0; lv < nlevels; ++lv) {
+        LevelPlan& P = plan[lv];
+        std::vector<int> sns;
+        for (int m = 0; m < nmat; ++m) {
+            const Symbolic& S = sym[m];
+            if (lv >= S.nlevels) continue;
+            for (int i = S.level_ptr[lv]; i < S.level_ptr[lv + 1]; ++i) sns.push_back(sn_off[m] + S.level_list[i]);
+        }
+        // extend-add
+        P.extend.off = (int)tasks.size();
+        for (int s : sns)
+            if (sn[s].child_end > sn[s].child_begin)
+                for (int a = 0; a * 64 < sn[s].m; ++a) push2(s, a);
+        P.extend.cnt = ((int)tasks.size() - P.extend.off) / 2;
+        int maxsteps = 0;
+        for (int s : sns) maxsteps = std::max(maxsteps, (sn[s].ns + NB - 1) / NB);
+        P.potrf.assign(maxsteps, Span());
+        P.trsm.assign(maxsteps, Span());
+        P.update.assign(maxsteps, Span());
+        for (int kb = 0; kb < maxsteps; ++kb) {
+            P.potrf[kb].off = (int)tasks.size();
+            for (int s : sns)
+                if (kb * NB < sn[s].ns) tasks.push_back(s);
+            P.potrf[kb].cnt = (int)tasks.size() - P.potrf[kb].off;
+            P.trsm[kb].off = (int)tasks.size();
+            for (int s : sns)
+                if (kb * NB < sn[s].ns)
+                    for (int a = 0; std::min((kb + 1) * NB, sn[s].ns) + a * 64 < sn[s].m; ++a) push2(s, a);
+            P.trsm[kb].cnt = ((int)tasks.size() - P.trsm[kb].off) / 2;
+            P.update[kb].off = (int)tasks.size();
+            for (int s : sns)
+                if (kb * NB < sn[s].ns) {
+                    int nt = 0;
+                    while (std::min((kb + 1) * NB, sn[s].ns) + nt * 64 < sn[s].m) ++nt;
+                    for (int a = 0; a < nt; ++a)
+                        for (int b = 0; b <= a; ++b) push2(s, (a & 0xffff) | (b << 16));
+                }
+            P.update[kb].cnt = ((int)tasks.size() - P.update[kb].off) / 2;
+        }
+        P.fwd_top.off = (int)tasks.size();
+        for (int s : sns) tasks.push_back(s);
+        P.fwd_top.cnt = (int)sns.size();
+        P.bwd_top = P.fwd_top;
+        P.fwd_below.off = (int)tasks.size();
+        for (int s : sns)
+            for (int a = 0; a * 64 < sn[s].m - sn[s].ns; ++a) push2(s, a);
+        P.fwd_below.cnt = ((int)tasks.size() - P.fwd_below.off) / 2;
+        P.bwd_below.off = (int)tasks.size();
+        for (int s : sns)
+            if (sn[s].m > sn[s].ns)
+                for (int a = 0; a * 64 < sn[s].ns; ++a) push2(s, a);
+        P.bwd_below.cnt = ((int)tasks.size() - P.bwd_below.off) / 2;
+    }
+    if (tasks.empty()) tasks.push_back(0);
+
+    d_sn.upload(sn, st);
+    d_rows.upload(rows, st);
+    d_rel.upload(rel, st);
+    if (child.empty()) child.push_back(0);
+    d_child.upload(child, st);
+    d_amap.upload(amap, st);
+    d_ea_ptr.upload(ea_ptr, st);
+    if (ea_src.empty()) ea_src.push_back(0);
+    d_ea_src.upload(ea_src, st);
+    d_tasks.upload(tasks, st);
+    L.alloc(std::max<int64_t>(nnz_l_total, 1));
+    CB.alloc(std::max<int64_t>(cb_total, 1));
+    tinv.alloc(std::max<int64_t>(tinv_total, 1));
+    ywork.alloc(n_total);
+    xwork.alloc(n_total);
+    rwork.alloc(n_total);
+    uwork.alloc(std::max<int64_t>(u_total, 1));
+    d_status.alloc(1);
+    d_status.zero(st);
+    int max_ns = 0;
+    for (auto& S : sym) max_ns = std::max(max_ns, S.max_nscol);
+    size_t shm_top = (size_t)(max_ns + 64) * sizeof(double);
+    DG_REQUIRE(shm_top <= 200 * 1024, "supernode too wide for the solve kernels' shared memory");
+    DG_CUDA(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
+    DG_CUDA(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
+    DG_CUDA(cudaFuncSetAttribute(k_fwd_below, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
+    DG_CUDA(cudaStreamSynchronize(st));
+    factorized = false;
+}
+
+int64_t CholBatch::device_bytes() const {
+    return (int64_t)(L.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
+                     d_amap.bytes() + d_ea_ptr.bytes() + d_ea_src.bytes() + d_tasks.bytes() + d_sn.bytes());
+}
+
+void CholBatch::factorize(const double* a_all, cudaStream_t st) {
+    DG_CUDA(cudaMemsetAsync(L.p, 0, L.bytes(), st));
+    DG_CUDA(cudaMemsetAsync(CB.p, 0, CB.bytes(), st));
+    DG_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), st));
+    if (nnz_a_total > 0) {
+        k_scatter_a<<<ceil_div(nnz_a_total, 256), 256, 0, st>>>(nnz_a_total, d_amap.p, a_all, L.p);
+        count_launch();
+    }
+    const int* T = d_tasks.p;
+    for (int lv = 0; lv < nlevels; ++lv) {
+        const LevelPlan& P = plan[lv];
+        if (P.extend.cnt) {
+            k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task2*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p);
+            count_launch();
+        }
+        for (size_t kb = 0; kb < P.potrf.size(); ++kb) {
+            if (P.potrf[kb].cnt) {
+                k_potrf<<<P.potrf[kb].cnt, 256, POTRF_SMEM, st>>>(T + P.potrf[kb].off, (int)kb, d_sn.p, L.p, tinv.p,
+                                                                                 d_status.p);
+                count_launch();
+            }
+            if (P.trsm[kb].cnt) {
+                k_trsm<<<P.trsm[kb].cnt, 128, 0, st>>>((const Task2*)(T + P.trsm[kb].off), (int)kb, d_sn.p, L.p, tinv.p);
+                count_launch();
+            }
+            if (P.update[kb].cnt) {
+                k_update<<<P.update[kb].cnt, 128, 0, st>>>((const Task3*)(T + P.update[kb].off), (int)kb, d_sn.p, L.p, CB.p);
+                count_launch();
+            }
+        }
+    }
+    factorized = true;
+}
+
+void CholBatch::check_status(cudaStream_t st) {
+    int h = 0;
+    DG_CUDA(cudaMemcpyAsync(&h, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    if (h != 0) throw Error(DOTGPU_ERR_NOT_SPD, "matrix not positive definite (supernode " + std::to_string(h - 1) + ")");
+}
+
+void CholBatch::solve(const double* b_perm, double* x_perm, cudaStream_t st) {
+    if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
+    const int* T = d_tasks.p;
+    int max_ns = 0;
+    for (auto& S : sym) max_ns = std::max(max_ns, S.max_nscol);
+    const size_t shm = (size_t)(max_ns + 64) * sizeof(double);
+    for (int lv = 0; lv < nlevels; ++lv) {
+        const LevelPlan& P = plan[lv];
+        if (P.fwd_top.cnt) {
+            k_fwd_top<<<P.fwd_top.cnt, 256, shm, st>>>(T + P.fwd_top.off, d_sn.p, d_ea_ptr.p, d_ea_src.p, L.p, tinv.p, b_perm, uwork.p,
+                                                       ywork.p);
+            count_launch();
+        }
+        if (P.fwd_below.cnt) {
+            k_fwd_below<<<P.fwd_below.cnt, 256, shm, st>>>((const Task2*)(T + P.fwd_below.off), d_sn.p, d_ea_ptr.p, d_ea_src.p, L.p,
+                                                           ywork.p, uwork.p);
+            count_launch();
+        }
+    }
+    for (int lv = nlevels - 1; lv >= 0; --lv) {
+        const LevelPlan& P = plan[lv];
+        if (P.bwd_below.cnt) {
+            k_bwd_below<<<P.bwd_below.cnt, 256, 0, st>>>((const Task2*)(T + P.bwd_below.off), d_sn.p, d_rows.p, L.p, xwork.p, rwork.p);
+            count_launch();
+        }
+        if (P.bwd_top.cnt) {
+            k_bwd_top<<<P.bwd_top.cnt, 256, shm, st>>>(T + P.bwd_top.off, d_sn.p, L.p, tinv.p, ywork.p, rwork.p, xwork.p);
+            count_launch();
+        }
+    }
+    DG_CUDA(cudaMemcpyAsync(x_perm, xwork.p, n_total * sizeof(double), cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace dotgpu

@@ -1,0 +1,43 @@
+// Device-resident tet mesh (the static part of Mesh<3>, Mesh.hpp:39-60) and the per-tet kernels'
+// launchers.  Layout in HBM:
+//   tets     int4[nT]            one 16-B load per thread
+//   DmInv    double[9][nT]       SoA -> coalesced across a warp of tets
+//   vol,mu,lam double[nT]
+//   vf_ptr/vf_idx                CSR of vFLoc: per vertex, ascending (tet*4+corner)  (Mesh.cpp:606-611)
+//   ge       double[12][nT]      elemental gradients (SoA), scratch
+//   He       double[nT][16][9]   elemental Hessians as 4x4 blocks of 3x3 (72 contiguous bytes per block)
+#pragma once
+#include "common.h"
+
+namespace dotgpu {
+
+struct DeviceMesh {
+    int nV = 0, nT = 0, energy = 0;
+    DevBuf<int> tets;       // 4*nT
+    DevBuf<double> DmInv;   // 9*nT SoA
+    DevBuf<double> vol, mu, lam;
+    DevBuf<double> mass;    // nV (may be empty for the bare energy object)
+    DevBuf<unsigned char> fixed;  // nV
+    DevBuf<int> vf_ptr, vf_idx;
+    DevBuf<double> ge;      // 12*nT
+    DevBuf<double> He;      // 144*nT, allocated on first use
+    DevBuf<double> partial; // block partial sums for reductions
+    int n_partial = 0;
+
+    void init(int energy_type, int nV_, int nT_, const int32_t* tets_h, const double* DmInv_rowmajor, const double* vol_h,
+              const double* mu_h, const double* lam_h, const double* mass_h, const unsigned char* fixed_h, cudaStream_t st);
+    void set_fixed(const unsigned char* fixed_h, cudaStream_t st);
+};
+
+// E_out[0] = coef * sum_t vol_t Psi_t(x)  + (xTilde ? sum_v m_v |x_v - xTilde_v|^2 / 2 : 0)    (device scalar)
+void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st);
+void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st);
+// g = gather(elemental gradients) [+ m (x - xTilde) on free vertices]; fixed entries zero
+void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st);
+void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st);
+// fills m.He ([nT][16][9])
+void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st);
+// converts m.He to the reference's row-major 12x12 layout
+void launch_he_to_dense(DeviceMesh& m, double* out144, cudaStream_t st);
+
+}  // namespace dotgpu

@@ -1,0 +1,342 @@
+// Per-tet kernels K1 (energy), K2 (gradient), K3 (elemental projected Hessians) + SVD dump.
+// One thread per tet; SoA loads coalesce across the warp; vertex positions are gathered through L2
+// (3*nV doubles are L2-resident for every mesh this path targets).  Reductions are deterministic
+// (fixed-shape block tree + a single-CTA final pass); the vertex gather sums elemental
+// contributions in ascending tet order like Energy.cpp:543-563.
+#include "device_mesh.h"
+#include "elastic.cuh"
+
+namespace dotgpu {
+
+thread_local int64_t g_launch_count = 0;
+
+namespace {
+
+constexpr int TPB = 128;
+
+struct TetIn {
+    Mat3 F;
+    double B[9];  // Dm^-1 row-major
+    double vol, mu, lam;
+    int v[4];
+};
+
+__device__ __forceinline__ void load_tet(int t, int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                         const double* __restrict__ vol, const double* __restrict__ mu,
+                                         const double* __restrict__ lam, const double* __restrict__ x, TetIn& o) {
+    int4 id = tets[t];
+    o.v[0] = id.x; o.v[1] = id.y; o.v[2] = id.z; o.v[3] = id.w;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) o.B[j] = DmInv[(size_t)j * nT + t];
+    o.vol = vol[t]; o.mu = mu[t]; o.lam = lam[t];
+    double x0[3], d[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x0[c] = x[3 * (size_t)id.x + c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        d[0][c] = x[3 * (size_t)id.y + c] - x0[c];
+        d[1][c] = x[3 * (size_t)id.z + c] - x0[c];
+        d[2][c] = x[3 * (size_t)id.w + c] - x0[c];
+    }
+    // F = Ds Dm^-1, Ds columns = d[k]:  F(i,j) = sum_k d[k][i] B[k][j]
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.F(i, j) = d[0][i] * o.B[j] + d[1][i] * o.B[3 + j] + d[2][i] * o.B[6 + j];
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0
+template <int N>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 32; ++i) r += sh[i];
+    }
+    return r;
+}
+
+template <int EN>
+__global__ void __launch_bounds__(TPB) k_energy(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                                const double* __restrict__ vol, const double* __restrict__ mu,
+                                                const double* __restrict__ lam, const double* __restrict__ x,
+                                                double* __restrict__ partial, double* __restrict__ per_elem) {
+    __shared__ double sh[TPB / 32];
+    int t = blockIdx.x * TPB + threadIdx.x;
+    double e = 0.0;
+    if (t < nT) {
+        TetIn in;
+        load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+        e = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
+        if (per_elem) per_elem[t] = e;
+    }
+    double s = block_sum<TPB>(e, sh);
+    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = s;
+}
+
+// inertia energy sum_v m_v |x_v - xTilde_v|^2 / 2 over ALL vertices (Optimizer.cpp:1204-1211)
+__global__ void __launch_bounds__(256) k_inertia_energy(int nV, const double* __restrict__ x, const double* __restrict__ xt,
+                                                        const double* __restrict__ mass, double* __restrict__ partial) {
+    __shared__ double sh[8];
+    int v = blockIdx.x * 256 + threadIdx.x;
+    double e = 0.0;
+    if (v < nV) {
+        double a = x[3 * (size_t)v] - xt[3 * (size_t)v], b = x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1],
+               c = x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2];
+        e = (a * a + b * b + c * c) * mass[v] / 2.0;
+    }
+    double s = block_sum<256>(e, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// out = coef * sum(partial[0..n1)) + sum(partial[n1..n1+n2))   single CTA, fixed order
+__global__ void __launch_bounds__(256) k_final_sum(const double* __restrict__ partial, int n1, int n2, double coef,
+                                                   double* __restrict__ out) {
+    __shared__ double sh[8];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n1; i += 256) a += partial[i];
+    for (int i = threadIdx.x; i < n2; i += 256) b += partial[n1 + i];
+    double sa = block_sum<256>(a, sh);
+    __syncthreads();
+    double sb = block_sum<256>(b, sh);
+    if (threadIdx.x == 0) out[0] = coef * sa + sb;
+}
+
+template <int EN>
+__global__ void __launch_bounds__(TPB) k_elem_grad(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                                   const double* __restrict__ vol, const double* __restrict__ mu,
+                                                   const double* __restrict__ lam, const double* __restrict__ x, double coef,
+                                                   double* __restrict__ ge) {
+    int t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= nT) return;
+    TetIn in;
+    load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+    Mat3 P;
+    double psi;
+    first_piola<EN>(in.F, in.mu, in.lam, P, psi);
+    double w = coef * in.vol;
+    // g_e[3+3a+b] = w * Dm^-1.row(a) . P.row(b)   (IglUtils.cpp:857-868)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double g0 = w * (in.B[3 * a] * P(0, 0) + in.B[3 * a + 1] * P(0, 1) + in.B[3 * a + 2] * P(0, 2));
+        double g1 = w * (in.B[3 * a] * P(1, 0) + in.B[3 * a + 1] * P(1, 1) + in.B[3 * a + 2] * P(1, 2));
+        double g2 = w * (in.B[3 * a] * P(2, 0) + in.B[3 * a + 1] * P(2, 1) + in.B[3 * a + 2] * P(2, 2));
+        ge[(size_t)(3 + 3 * a) * nT + t] = g0;
+        ge[(size_t)(4 + 3 * a) * nT + t] = g1;
+        ge[(size_t)(5 + 3 * a) * nT + t] = g2;
+        s0 += g0; s1 += g1; s2 += g2;
+    }
+    ge[t] = -s0;
+    ge[(size_t)nT + t] = -s1;
+    ge[(size_t)2 * nT + t] = -s2;
+}
+
+__global__ void __launch_bounds__(256) k_vertex_gather(int nV, int nT, const int* __restrict__ vf_ptr, const int* __restrict__ vf_idx,
+                                                       const double* __restrict__ ge, const unsigned char* __restrict__ fixed,
+                                                       const double* __restrict__ x, const double* __restrict__ xt,
+                                                       const double* __restrict__ mass, double* __restrict__ g) {
+    int v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= nV) return;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (!fixed[v]) {
+        int b = vf_ptr[v], e = vf_ptr[v + 1];
+        for (int i = b; i < e; ++i) {
+            int code = vf_idx[i];
+            int t = code >> 2, k = code & 3;
+            g0 += ge[(size_t)(3 * k) * nT + t];
+            g1 += ge[(size_t)(3 * k + 1) * nT + t];
+            g2 += ge[(size_t)(3 * k + 2) * nT + t];
+        }
+        if (xt) {  // Optimizer.cpp:1239-1252
+            double m = mass[v];
+            g0 += m * (x[3 * (size_t)v] - xt[3 * (size_t)v]);
+            g1 += m * (x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1]);
+            g2 += m * (x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2]);
+        }
+    }
+    g[3 * (size_t)v] = g0;
+    g[3 * (size_t)v + 1] = g1;
+    g[3 * (size_t)v + 2] = g2;
+}
+
+__global__ void __launch_bounds__(TPB) k_svd(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                             const double* __restrict__ vol, const double* __restrict__ mu,
+                                             const double* __restrict__ lam, const double* __restrict__ x, double* Fo, double* Uo,
+                                             double* So, double* Vo) {
+    int t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= nT) return;
+    TetIn in;
+    load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+    Mat3 U, V;
+    double S[3];
+    svd3(in.F, U, S, V);
+    for (int i = 0; i < 9; ++i) {
+        if (Fo) Fo[(size_t)9 * t + i] = in.F.m[i];
+        if (Uo) Uo[(size_t)9 * t + i] = U.m[i];
+        if (Vo) Vo[(size_t)9 * t + i] = V.m[i];
+    }
+    if (So) for (int i = 0; i < 3; ++i) So[(size_t)3 * t + i] = S[i];
+}
+
+template <int EN>
+__global__ void __launch_bounds__(TPB) k_hessian(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                                 const double* __restrict__ vol, const double* __restrict__ mu,
+                                                 const double* __restrict__ lam, const double* __restrict__ x, double coef,
+                                                 int project, double* __restrict__ He) {
+    int t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= nT) return;
+    TetIn in;
+    load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+    Mat3 U, V;
+    double S[3];
+    svd3(in.F, U, S, V);
+    HessCoef hc;
+    hess_coef<EN>(S, in.mu, in.lam, coef * in.vol, project != 0, hc);
+    // beta[k][b] = v_b . w_k,  w_k = row k-1 of Dm^-1 (k=1..3), w_0 = -(sum of rows)
+    double beta[4][3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            beta[k + 1][b] = in.B[3 * k] * V(0, b) + in.B[3 * k + 1] * V(1, b) + in.B[3 * k + 2] * V(2, b);
+        beta[0][b] = -(beta[1][b] + beta[2][b] + beta[3][b]);
+    }
+    double* out = He + (size_t)144 * t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int l = k; l < 4; ++l) {
+            double blk[9];
+            hess_block(hc, U, beta[k], beta[l], blk);
+            if (k == l) {  // symmetrise the diagonal block exactly (the reference mirrors the upper part, Energy.cpp:1263-1265)
+                blk[3] = blk[1]; blk[6] = blk[2]; blk[7] = blk[5];
+            }
+            double2* o2;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) out[(4 * k + l) * 9 + i] = blk[i];
+            if (l != k) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) out[(4 * l + k) * 9 + 3 * r + i] = blk[3 * i + r];
+            }
+            (void)o2;
+        }
+    }
+}
+
+// [nT][16][9] block layout -> row-major 12x12
+__global__ void k_he_to_dense(int nT, const double* __restrict__ He, double* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nT * 144) return;
+    int t = (int)(i / 144), e = (int)(i % 144);
+    int row = e / 12, col = e % 12;
+    int k = row / 3, ii = row % 3, l = col / 3, r = col % 3;
+    out[i] = He[(size_t)144 * t + (4 * k + l) * 9 + 3 * ii + r];
+}
+
+}  // namespace
+
+void DeviceMesh::init(int energy_type, int nV_, int nT_, const int32_t* tets_h, const double* DmInv_rm, const double* vol_h,
+                      const double* mu_h, const double* lam_h, const double* mass_h, const unsigned char* fixed_h,
+                      cudaStream_t st) {
+    DG_REQUIRE(energy_type == DOTGPU_ENERGY_FCR || energy_type == DOTGPU_ENERGY_SNH, "unknown energy type");
+    DG_REQUIRE(nV_ > 0 && nT_ > 0, "empty mesh");
+    energy = energy_type;
+    nV = nV_;
+    nT = nT_;
+    for (size_t i = 0; i < (size_t)4 * nT; ++i) DG_REQUIRE(tets_h[i] >= 0 && tets_h[i] < nV, "tet index out of range");
+    tets.upload(tets_h, (size_t)4 * nT, st);
+    std::vector<double> soa((size_t)9 * nT);
+    for (int t = 0; t < nT; ++t)
+        for (int j = 0; j < 9; ++j) soa[(size_t)j * nT + t] = DmInv_rm[(size_t)9 * t + j];
+    DmInv.upload(soa, st);
+    vol.upload(vol_h, nT, st);
+    mu.upload(mu_h, nT, st);
+    lam.upload(lam_h, nT, st);
+    if (mass_h) mass.upload(mass_h, nV, st);
+    std::vector<unsigned char> fx(nV, 0);
+    if (fixed_h) fx.assign(fixed_h, fixed_h + nV);
+    fixed.upload(fx, st);
+    // vFLoc as CSR, ascending tet (Mesh.cpp:606-611)
+    std::vector<int> ptr(nV + 1, 0);
+    for (size_t i = 0; i < (size_t)4 * nT; ++i) ptr[tets_h[i] + 1]++;
+    for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int> idx((size_t)4 * nT), cur(ptr.begin(), ptr.end() - 1);
+    for (int t = 0; t < nT; ++t)
+        for (int k = 0; k < 4; ++k) idx[cur[tets_h[4 * t + k]]++] = 4 * t + k;
+    vf_ptr.upload(ptr, st);
+    vf_idx.upload(idx, st);
+    ge.alloc((size_t)12 * nT);
+    n_partial = ceil_div(nT, TPB) + ceil_div(nV, 256);
+    partial.alloc(n_partial);
+    DG_CUDA(cudaStreamSynchronize(st));
+}
+
+void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
+    fixed.upload(fixed_h, nV, st);
+    DG_CUDA(cudaStreamSynchronize(st));
+}
+
+#define DISPATCH_EN(m, KERNEL, grid, block, st, ...)                           \
+    do {                                                                       \
+        if ((m).energy == DOTGPU_ENERGY_FCR)                                   \
+            KERNEL<DG_FCR><<<grid, block, 0, st>>>(__VA_ARGS__);               \
+        else                                                                   \
+            KERNEL<DG_SNH><<<grid, block, 0, st>>>(__VA_ARGS__);               \
+        count_launch();                                                        \
+    } while (0)
+
+void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st) {
+    int nb = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_energy, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, m.partial.p,
+                (double*)nullptr);
+    int nb2 = 0;
+    if (xTilde) {
+        nb2 = ceil_div(m.nV, 256);
+        k_inertia_energy<<<nb2, 256, 0, st>>>(m.nV, x, xTilde, m.mass.p, m.partial.p + nb);
+        count_launch();
+    }
+    k_final_sum<<<1, 256, 0, st>>>(m.partial.p, nb, nb2, coef, E_out);
+    count_launch();
+}
+
+void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st) {
+    int nb = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_energy, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
+                (double*)nullptr, out);
+}
+
+void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st) {
+    int nb = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_elem_grad, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.ge.p);
+    k_vertex_gather<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.nT, m.vf_ptr.p, m.vf_idx.p, m.ge.p, m.fixed.p, x, xTilde,
+                                                         m.mass.p, g);
+    count_launch();
+}
+
+void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st) {
+    k_svd<<<ceil_div(m.nT, TPB), TPB, 0, st>>>(m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, F, U, S, V);
+    count_launch();
+}
+
+void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st) {
+    if (m.He.n < (size_t)144 * m.nT) m.He.alloc((size_t)144 * m.nT);
+    int nb = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_hessian, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef,
+                project ? 1 : 0, m.He.p);
+}
+
+void launch_he_to_dense(DeviceMesh& m, double* out144, cudaStream_t st) {
+    size_t n = (size_t)m.nT * 144;
+    k_he_to_dense<<<ceil_div(n, 256), 256, 0, st>>>(m.nT, m.He.p, out144);
+    count_launch();
+}
+
+}  // namespace dotgpu

@@ -1,0 +1,260 @@
+#include "linalg.h"
+
+namespace dotgpu {
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic CTA sum for 256 threads, valid in thread 0
+__device__ __forceinline__ double cta_sum256(double v, double* sh) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) r = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_fill(long long nblk, const long long* __restrict__ ptr, const int* __restrict__ src,
+                                              const int* __restrict__ row, const int* __restrict__ bj, const double* __restrict__ consts,
+                                              const int* __restrict__ ia, const double* __restrict__ He, double* __restrict__ a) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    double acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    for (long long e = ptr[b]; e < ptr[b + 1]; ++e) {
+        int code = src[e];
+        if (code >= 0) {
+            const double* __restrict__ h = He + (long long)code * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[i] += h[i];
+        } else {
+            double c = consts[-code - 1];
+            acc[0] += c; acc[4] += c; acc[8] += c;
+        }
+    }
+    const int r = row[b], j = bj[b];
+    if (j < 0) {  // fixed vertex: three 1x1 rows
+        a[ia[r]] = acc[0];
+        a[ia[r + 1]] = acc[4];
+        a[ia[r + 2]] = acc[8];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int base = ia[r + i] + 3 * j - i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (j > 0 || c >= i) a[base + c] = acc[3 * i + c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_quadform(int n, const int* __restrict__ ia, const int* __restrict__ ja, const double* __restrict__ a,
+                                                  const double* __restrict__ p, double* __restrict__ partial) {
+    __shared__ double sh[8];
+    int i = blockIdx.x * 256 + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        const double pi = p[i];
+        int b = ia[i], e = ia[i + 1];
+        double off = 0.0;
+        for (int k = b + 1; k < e; ++k) off += a[k] * p[ja[k]];
+        s = pi * (a[b] * pi + 2.0 * off);  // first entry of every row is the diagonal
+    }
+    double r = cta_sum256(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    double r = cta_sum256(s, sh);
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+__global__ void __launch_bounds__(256) k_spmv_sym(int n, const int* __restrict__ ia, const int* __restrict__ ja, const double* __restrict__ a,
+                                                  const int* __restrict__ tp, const int* __restrict__ tslot, const int* __restrict__ trow,
+                                                  const double* __restrict__ x, double* __restrict__ y) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = tp[i]; k < tp[i + 1]; ++k) s += a[tslot[k]] * x[trow[k]];  // strictly-lower part via the transposed index
+    for (int k = ia[i]; k < ia[i + 1]; ++k) s += a[k] * x[ja[k]];
+    y[i] = s;
+}
+
+constexpr int DOT_TPB = 256;
+constexpr int DOT_MAX_BLOCKS = 592;  // 4 CTAs per SM
+
+__global__ void __launch_bounds__(DOT_TPB) k_dot(long long n, const double* __restrict__ a, const double* __restrict__ b,
+                                                 double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double sh[8];
+    __shared__ bool last;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * DOT_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * DOT_TPB) s += a[i] * b[i];
+    double r = cta_sum256(s, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = r;
+        __threadfence();
+        unsigned t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {  // the last CTA to finish sums the partials in a fixed order
+        __threadfence();
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += DOT_TPB) v += ((volatile double*)partial)[i];
+        __syncthreads();
+        double tot = cta_sum256(v, sh);
+        if (threadIdx.x == 0) {
+            out[0] = tot;
+            *counter = 0u;
+        }
+    }
+}
+
+__global__ void k_axpy_sc(long long n, double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ sc, int num, int den,
+                          double sign) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c = sign * sc[num] / (den >= 0 ? sc[den] : 1.0);
+    y[i] += c * x[i];
+}
+
+__global__ void k_lbfgs_first(long long n, double* __restrict__ q, const double* __restrict__ y, double* __restrict__ sc, int dot, int ys,
+                              int ksi) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double k = sc[dot] / sc[ys];
+    if (i < n) q[i] -= k * y[i];
+    if (i == 0) sc[ksi] = k;  // read by the second loop (launched later on the same stream)
+}
+
+__global__ void k_lbfgs_second(long long n, double* __restrict__ p, const double* __restrict__ s, const double* __restrict__ sc, int dot,
+                               int ys, int ksi) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] += s[i] * (sc[ksi] - sc[dot] / sc[ys]);
+}
+
+__global__ void k_scale_copy(long long n, double* __restrict__ out, const double* __restrict__ in, double alpha) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = alpha * in[i];
+}
+__global__ void k_axpy(long long n, double* __restrict__ out, const double* __restrict__ x0, const double* __restrict__ p, double alpha) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x0[i] + alpha * p[i];
+}
+__global__ void k_sub(long long n, double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+__global__ void k_warm_start(int nV, double* __restrict__ x, const double* __restrict__ vel, const unsigned char* __restrict__ fixed, double dt,
+                             double gx, double gy, double gz) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV || fixed[v]) return;
+    x[3 * (size_t)v] = x[3 * (size_t)v] + 1.0 * (dt * vel[3 * (size_t)v] + gx);
+    x[3 * (size_t)v + 1] = x[3 * (size_t)v + 1] + 1.0 * (dt * vel[3 * (size_t)v + 1] + gy);
+    x[3 * (size_t)v + 2] = x[3 * (size_t)v + 2] + 1.0 * (dt * vel[3 * (size_t)v + 2] + gz);
+}
+__global__ void k_xtilde(int nV, double* __restrict__ xt, const double* __restrict__ xn, const double* __restrict__ vel,
+                         const unsigned char* __restrict__ fixed, double dt, double gx, double gy, double gz) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const bool f = fixed[v];
+    xt[3 * (size_t)v] = f ? xn[3 * (size_t)v] : xn[3 * (size_t)v] + (vel[3 * (size_t)v] * dt + gx);
+    xt[3 * (size_t)v + 1] = f ? xn[3 * (size_t)v + 1] : xn[3 * (size_t)v + 1] + (vel[3 * (size_t)v + 1] * dt + gy);
+    xt[3 * (size_t)v + 2] = f ? xn[3 * (size_t)v + 2] : xn[3 * (size_t)v + 2] + (vel[3 * (size_t)v + 2] * dt + gz);
+}
+__global__ void k_velocity(long long n, double* __restrict__ vel, const double* __restrict__ x, const double* __restrict__ xn, double dt) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vel[i] = (x[i] - xn[i]) / dt;
+}
+__global__ void k_gather(long long n, const int* __restrict__ gidx, const double* __restrict__ q, double* __restrict__ b) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = q[gidx[i]];
+}
+__global__ void k_scatter_avg(int ndof, const int* __restrict__ cptr, const int* __restrict__ cidx, const double* __restrict__ xs,
+                              const int* __restrict__ dup, double* __restrict__ p) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    double s = 0.0;
+    for (int k = cptr[d]; k < cptr[d + 1]; ++k) s += xs[cidx[k]];
+    int du = dup ? dup[d / 3] : 1;
+    if (du > 1) s /= (double)du;
+    p[d] = s;
+}
+
+}  // namespace
+
+void launch_fill(const DeviceFill& f, const double* He, double* a, cudaStream_t st) {
+    if (!f.nblk) return;
+    k_fill<<<ceil_div(f.nblk, 128), 128, 0, st>>>(f.nblk, f.ptr.p, f.src.p, f.row.p, f.j.p, f.consts.p, f.ia.p, He, a);
+    count_launch();
+}
+
+void launch_quadform(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, double* out, cudaStream_t st) {
+    int nb = ceil_div(n, 256);
+    k_quadform<<<nb, 256, 0, st>>>(n, ia, ja, a, p, partial);
+    k_sum_partials<<<1, 256, 0, st>>>(partial, nb, out);
+    count_launch(2);
+}
+
+void launch_spmv_sym(int n, const int* ia, const int* ja, const double* a, const int* tp, const int* tslot, const int* trow, const double* x,
+                     double* y, cudaStream_t st) {
+    k_spmv_sym<<<ceil_div(n, 256), 256, 0, st>>>(n, ia, ja, a, tp, tslot, trow, x, y);
+    count_launch();
+}
+
+int dot_partial_count(long long) { return DOT_MAX_BLOCKS; }
+
+void launch_dot(long long n, const double* a, const double* b, double* partial, unsigned* counter, double* sc_out, cudaStream_t st) {
+    int nb = (int)std::min<long long>(DOT_MAX_BLOCKS, std::max<long long>(1, (n + DOT_TPB * 4 - 1) / (DOT_TPB * 4)));
+    k_dot<<<nb, DOT_TPB, 0, st>>>(n, a, b, partial, counter, sc_out);
+    count_launch();
+}
+
+#define EW_LAUNCH(kernel, n, ...)                                              \
+    do {                                                                       \
+        if ((n) > 0) {                                                         \
+            kernel<<<ceil_div((n), 256), 256, 0, st>>>(__VA_ARGS__);           \
+            count_launch();                                                    \
+        }                                                                      \
+    } while (0)
+
+void launch_axpy_sc(long long n, double* y, const double* x, const double* sc, int num, int den, double sign, cudaStream_t st) {
+    EW_LAUNCH(k_axpy_sc, n, n, y, x, sc, num, den, sign);
+}
+void launch_lbfgs_first(long long n, double* q, const double* y, double* sc, int dot, int ys, int ksi, cudaStream_t st) {
+    EW_LAUNCH(k_lbfgs_first, n, n, q, y, sc, dot, ys, ksi);
+}
+void launch_lbfgs_second(long long n, double* p, const double* s, const double* sc, int dot, int ys, int ksi, cudaStream_t st) {
+    EW_LAUNCH(k_lbfgs_second, n, n, p, s, sc, dot, ys, ksi);
+}
+void launch_scale_copy(long long n, double* out, const double* in, double alpha, cudaStream_t st) { EW_LAUNCH(k_scale_copy, n, n, out, in, alpha); }
+void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st) {
+    EW_LAUNCH(k_axpy, n, n, out, x0, p, alpha);
+}
+void launch_sub(long long n, double* out, const double* a, const double* b, cudaStream_t st) { EW_LAUNCH(k_sub, n, n, out, a, b); }
+void launch_warm_start(int nV, double* x, const double* vel, const unsigned char* fixed, double dt, double gx, double gy, double gz,
+                       cudaStream_t st) {
+    EW_LAUNCH(k_warm_start, nV, nV, x, vel, fixed, dt, gx, gy, gz);
+}
+void launch_xtilde(int nV, double* xt, const double* xn, const double* vel, const unsigned char* fixed, double dt, double gx, double gy,
+                   double gz, cudaStream_t st) {
+    EW_LAUNCH(k_xtilde, nV, nV, xt, xn, vel, fixed, dt, gx, gy, gz);
+}
+void launch_velocity(int nV, double* vel, const double* x, const double* xn, double dt, cudaStream_t st) {
+    long long n = 3LL * nV;
+    EW_LAUNCH(k_velocity, n, n, vel, x, xn, dt);
+}
+void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st) { EW_LAUNCH(k_gather, n, n, gidx, q, b); }
+void launch_scatter_avg(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, cudaStream_t st) {
+    EW_LAUNCH(k_scatter_avg, ndof, ndof, cptr, cidx, xs, dup, p);
+}
+
+}  // namespace dotgpu

@@ -1,0 +1,55 @@
+// Matrix fill from elemental Hessians, symmetric SpMV / quadratic form on CSR-upper storage, and the
+// dense-vector kernels of the L-BFGS iteration (all scalars stay on the device).
+#pragma once
+#include "common.h"
+
+namespace dotgpu {
+
+// ---- matrix fill (DOTTimeStepper.cpp:574-616, 619-797 as ordered gather lists) ----
+struct DeviceFill {
+    long long nblk = 0;
+    DevBuf<long long> ptr;   // [nblk+1]
+    DevBuf<int> src;         // codes, see mesh_host.h
+    DevBuf<int> row;         // [nblk] index of scalar row 3v in the concatenated ia array
+    DevBuf<int> j;           // [nblk] block index within the row, -1 => fixed vertex (diagonal-only row)
+    DevBuf<double> consts;
+    DevBuf<int> ia;          // concatenated row pointers, already offset into the concatenated value array
+};
+void launch_fill(const DeviceFill& f, const double* He, double* a, cudaStream_t st);
+
+// ---- CSR-upper symmetric matrix (global Hessian, Optimizer::linSysSolver) ----
+// out[0] = p^T A p  (device scalar), deterministic
+void launch_quadform(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, double* out,
+                     cudaStream_t st);
+// y = A x with A symmetric given by its upper triangle; needs the transposed index (tp, ti = slot, tr = row)
+void launch_spmv_sym(int n, const int* ia, const int* ja, const double* a, const int* tp, const int* tslot, const int* trow,
+                     const double* x, double* y, cudaStream_t st);
+
+// ---- dense vectors; scalars live in a small device array `sc` ----
+int dot_partial_count(long long n);
+// sc[k] = a.b    (partial must hold dot_partial_count(n) doubles, counter one zeroed unsigned)
+void launch_dot(long long n, const double* a, const double* b, double* partial, unsigned* counter, double* sc_out, cudaStream_t st);
+// y += (sc[num] / sc[den]) * x * sign   (den < 0 => divisor 1)
+void launch_axpy_sc(long long n, double* y, const double* x, const double* sc, int num, int den, double sign, cudaStream_t st);
+// two-loop helpers (DOTTimeStepper.cpp:389-398, 459-466):
+//   first loop : ksi = (s.q)/ys ; q -= ksi*y      -> dot into sc[DOT], then this with coefficient sc[dot]/sc[ys], result stored to sc[ksi]
+void launch_lbfgs_first(long long n, double* q, const double* y, double* sc, int dot, int ys, int ksi, cudaStream_t st);
+//   second loop: p += s * (ksi - (y.p)/ys)
+void launch_lbfgs_second(long long n, double* p, const double* s, const double* sc, int dot, int ys, int ksi, cudaStream_t st);
+void launch_scale_copy(long long n, double* out, const double* in, double alpha, cudaStream_t st);            // out = alpha*in
+void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st);  // out = x0 + alpha*p
+void launch_sub(long long n, double* out, const double* a, const double* b, cudaStream_t st);                 // out = a - b
+// initX + xTilde (Optimizer.cpp:472-493, 585-610): x += (dt v + dt^2 g) on free verts
+void launch_warm_start(int nV, double* x, const double* vel, const unsigned char* fixed, double dt, double gx, double gy, double gz,
+                       cudaStream_t st);
+void launch_xtilde(int nV, double* xt, const double* xn, const double* vel, const unsigned char* fixed, double dt, double gx, double gy,
+                   double gz, cudaStream_t st);
+void launch_velocity(int nV, double* vel, const double* x, const double* xn, double dt, cudaStream_t st);
+
+// ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
+// b[i] = q[gidx[i]]  for the concatenated permuted right-hand sides
+void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st);
+// p[d] = (sum over the subdomain copies of dof d, in subdomain order) / dup
+void launch_scatter_avg(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, cudaStream_t st);
+
+}  // namespace dotgpu

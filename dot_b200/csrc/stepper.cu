@@ -1,0 +1,425 @@
+#include "stepper.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "comm.h"
+
+namespace dotgpu {
+
+namespace {
+__global__ void k_div_dup(int ndof, const int* __restrict__ dup, double* __restrict__ p) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    int du = dup[d / 3];
+    if (du > 1) p[d] /= (double)du;
+}
+__global__ void k_neg(long long n, double* __restrict__ out, const double* __restrict__ in) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+}  // namespace
+
+Stepper::~Stepper() {
+    if (h_sc) cudaFreeHost(h_sc);
+    if (h_x) cudaFreeHost(h_x);
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    comm.reset();
+    if (st) cudaStreamDestroy(st);
+}
+
+// ||d2Psi/dF2 (I)||_F^2 without projection (Optimizer.cpp:613-628 via compute_dP_div_dF at the identity)
+static double rest_hessian_sqnorm(int energy, double mu, double lam) {
+    double Ad, Ao, l, r;
+    if (energy == DOTGPU_ENERGY_FCR) {
+        Ad = 2.0 * mu + lam;
+        Ao = lam * (1.0 * (1.0 - 1.0) + 1.0);
+        l = mu - lam / 2.0 * 1.0 * (1.0 - 1.0);
+        double dE = 2.0 * mu * 0.0 + 1.0 * lam * 0.0;
+        r = (dE + dE) / (2.0 * 2.0);
+    } else {
+        double alpha = 1.0 + mu / lam;
+        Ad = mu + lam;
+        Ao = 1.0 * lam * (2.0 - alpha);
+        double t0 = lam * (1.0 - alpha);
+        l = (mu - t0 * 1.0) / 2.0;
+        double dE = 1.0 * mu + t0 * 1.0;
+        r = (dE + dE) / (2.0 * 2.0);
+    }
+    double s = 3.0 * Ad * Ad + 6.0 * Ao * Ao;
+    s += 3.0 * (2.0 * (l + r) * (l + r) + 2.0 * (l - r) * (l - r));
+    return s;
+}
+
+double Stepper::compute_target() const {
+    // Optimizer::computeCharNormSq (Optimizer.cpp:613-651), evaluated on data0 whose fixedVert is {0}
+    const double mu = cfg.YM / 2.0 / (1.0 + cfg.PR), lam = cfg.YM * cfg.PR / (1.0 + cfg.PR) / (1.0 - 2.0 * cfg.PR);
+    std::vector<double> ls(nV, 0.0);
+    for (int t = 0; t < nT; ++t) {
+        const int32_t* T = tets_h.data() + 4 * (size_t)t;
+        for (int j = 0; j < 4; ++j) {  // face opposite vertex j (igl::face_areas)
+            int o[3], c = 0;
+            for (int i = 0; i < 4; ++i)
+                if (i != j) o[c++] = T[i];
+            const double *a = &V_rest[3 * (size_t)o[0]], *b = &V_rest[3 * (size_t)o[1]], *cc = &V_rest[3 * (size_t)o[2]];
+            double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {cc[0] - a[0], cc[1] - a[1], cc[2] - a[2]};
+            double cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            ls[T[j]] += 0.5 * std::sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+        }
+    }
+    double sq = 0.0;
+    for (double v : ls) sq += v * v;
+    const double dt = cfg.dt;
+    double t = cfg.rel_tol * cfg.rel_tol * rest_hessian_sqnorm(cfg.energy_type, mu, lam) * sq * (nV - cfg.target_fixed_count) / nV;
+    return t * (dt * dt) * (dt * dt);
+}
+
+void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const double* Vr, const int32_t* T, const int32_t* ep,
+                     const uint8_t* fixed_mask) {
+    cfg = c;
+    nV = nV_;
+    nT = nT_;
+    DG_REQUIRE(nV > 0 && nT > 0 && Vr && T && ep, "null or empty mesh");
+    DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= 8, "bad subdomain count / history size");
+    DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
+    DG_REQUIRE(cfg.dt > 0, "dt must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DOTGPU_ERR_NO_DEVICE, "no CUDA device");
+    DG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device index out of range");
+    DG_CUDA(cudaSetDevice(cfg.device));
+    DG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) DG_CUDA(cudaEventCreate(&e));
+    launches0 = g_launch_count;
+    V_rest.assign(Vr, Vr + 3 * (size_t)nV);
+    tets_h.assign(T, T + 4 * (size_t)nT);
+    epart_h.assign(ep, ep + nT);
+    fixed_h.assign(nV, 0);
+    if (fixed_mask) fixed_h.assign(fixed_mask, fixed_mask + nV);
+
+    // ---- mesh features + upload ----
+    std::vector<double> DmInv(9 * (size_t)nT), vol(nT), mu(nT), lam(nT);
+    mass_h.assign(nV, 0.0);
+    mesh_features(nV, nT, V_rest.data(), tets_h.data(), cfg.YM, cfg.PR, cfg.rho, DmInv.data(), vol.data(), mass_h.data(), mu.data(),
+                  lam.data());
+    for (int t = 0; t < nT; ++t) DG_REQUIRE(vol[t] > 0.0, "inverted or degenerate rest tet");
+    mesh.init(cfg.energy_type, nV, nT, tets_h.data(), DmInv.data(), vol.data(), mu.data(), lam.data(), mass_h.data(), fixed_h.data(), st);
+
+    // ---- domain decomposition, owned subdomains ----
+    const int k = cfg.num_subdomains;
+    std::vector<char> mask(k, 0);
+    owned.clear();
+    for (int s = 0; s < k; ++s)
+        if (s % cfg.world == cfg.rank) {
+            mask[s] = 1;
+            owned.push_back(s);
+        }
+    dd.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), V_rest.data(), cfg.rho, mass_h.data(), true, &mask);
+
+    // ---- concatenated matrices: [global | owned subdomains] ----
+    const int nm = 1 + (int)owned.size();
+    a_off.assign(nm + 1, 0);
+    a_off[1] = dd.gpat.nnz();
+    for (size_t i = 0; i < owned.size(); ++i) a_off[2 + i] = a_off[1 + i] + dd.subs[owned[i]].pat.nnz();
+    DG_REQUIRE(a_off[nm] < (1LL << 31), "too many matrix entries for int32 slots");
+    a_all.alloc(a_off[nm]);
+    g_ia.upload(dd.gpat.ia, st);
+    g_ja.upload(dd.gpat.ja, st);
+    {
+        std::vector<long long> ptr(1, 0);
+        std::vector<int> src, row, bj, ia;
+        std::vector<double> consts;
+        auto add = [&](const MatrixPattern& P, const FillList& F, int64_t aoff) {
+            const int ia_base = (int)ia.size();
+            for (int32_t v : P.ia) ia.push_back((int)(v + aoff));
+            const int cbase = (int)consts.size();
+            consts.insert(consts.end(), F.consts.begin(), F.consts.end());
+            const long long sbase = (long long)src.size();
+            for (int32_t code : F.src) src.push_back(code >= 0 ? code : code - cbase);
+            for (size_t b = 1; b < F.ptr.size(); ++b) ptr.push_back(sbase + F.ptr[b]);
+            for (int v = 0; v < P.nverts; ++v)
+                for (int b = P.bptr[v]; b < P.bptr[v + 1]; ++b) {
+                    row.push_back(ia_base + 3 * v);
+                    bj.push_back(P.fixed[v] ? -1 : b - P.bptr[v]);
+                }
+        };
+        add(dd.gpat, dd.gfill, a_off[0]);
+        for (size_t i = 0; i < owned.size(); ++i) add(dd.subs[owned[i]].pat, dd.subs[owned[i]].fill, a_off[1 + i]);
+        fill.nblk = (long long)row.size();
+        DG_REQUIRE((long long)ptr.size() == fill.nblk + 1, "fill list size mismatch");
+        fill.ptr.upload(ptr, st);
+        fill.src.upload(src, st);
+        fill.row.upload(row, st);
+        fill.j.upload(bj, st);
+        fill.consts.upload(consts, st);
+        fill.ia.upload(ia, st);
+    }
+
+    // ---- symbolic analysis of the owned subdomain matrices ----
+    {
+        std::vector<const int32_t*> ia, ja;
+        std::vector<int> n;
+        for (int s : owned) {
+            ia.push_back(dd.subs[s].pat.ia.data());
+            ja.push_back(dd.subs[s].pat.ja.data());
+            n.push_back(dd.subs[s].pat.n());
+        }
+        chol.analyze(ia, ja, n, 21, st);
+    }
+    // ---- preconditioner gather / scatter maps ----
+    {
+        std::vector<int> gi(chol.n_total);
+        std::vector<std::vector<int>> copies(3 * (size_t)nV);
+        for (size_t i = 0; i < owned.size(); ++i) {
+            const SubdomainHost& sd = dd.subs[owned[i]];
+            const Symbolic& S = chol.sym[i];
+            for (int pnew = 0; pnew < S.n; ++pnew) {
+                int old = S.perm[pnew];
+                int gd = 3 * sd.l2g[old / 3] + old % 3;
+                gi[chol.col_off[i] + pnew] = gd;
+                copies[gd].push_back((int)(chol.col_off[i] + pnew));
+            }
+        }
+        std::vector<int> cp(3 * (size_t)nV + 1, 0), ci;
+        ci.reserve(chol.n_total);
+        for (size_t d = 0; d < copies.size(); ++d) {
+            ci.insert(ci.end(), copies[d].begin(), copies[d].end());  // ascending subdomain order (DOTTimeStepper.cpp:436-445)
+            cp[d + 1] = (int)ci.size();
+        }
+        if (ci.empty()) ci.push_back(0);
+        gidx.upload(gi, st);
+        cptr.upload(cp, st);
+        cidx.upload(ci, st);
+        std::vector<int> du(dd.dup.begin(), dd.dup.end());
+        dup.upload(du, st);
+    }
+    // ---- vectors ----
+    const size_t n3 = 3 * (size_t)nV;
+    for (DevBuf<double>* b : {&x, &x0, &xn, &xt, &vel, &g, &g_old, &q, &p}) {
+        b->alloc(n3);
+        b->zero(st);
+    }
+    bperm.alloc(std::max<int64_t>(chol.n_total, 1));
+    xperm.alloc(std::max<int64_t>(chol.n_total, 1));
+    qf_partial.alloc(ceil_div((long long)n3, 256) + 1);
+    dot_partial.alloc(dot_partial_count((long long)n3));
+    S.resize(cfg.history + 1);
+    Y.resize(cfg.history + 1);
+    for (int i = 0; i <= cfg.history; ++i) {
+        S[i].alloc(n3);
+        Y[i].alloc(n3);
+    }
+    sc.alloc(SC_COUNT);
+    sc.zero(st);
+    counter.alloc(1);
+    counter.zero(st);
+    DG_CUDA(cudaMallocHost((void**)&h_sc, SC_COUNT * sizeof(double)));
+    DG_CUDA(cudaMallocHost((void**)&h_x, n3 * sizeof(double)));
+    if (cfg.world > 1) {
+        comm.reset(new Comm());
+        comm->init(cfg.nccl_unique_id, cfg.rank, cfg.world);
+    }
+    target = compute_target();
+    // ---- precompute(): rest-state energy, Hessians, factorisation (DOTTimeStepper.cpp:150-182) ----
+    x.upload(V_rest.data(), n3, st);
+    DG_CUDA(cudaMemcpyAsync(xn.p, x.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    launch_xtilde(nV, xt.p, xn.p, vel.p, mesh.fixed.p, cfg.dt, cfg.gravity[0] * cfg.dt * cfg.dt, cfg.gravity[1] * cfg.dt * cfg.dt,
+                  cfg.gravity[2] * cfg.dt * cfg.dt, st);
+    refresh();
+    chol.check_status(st);
+}
+
+void Stepper::fetch_scalars(int first, int count) {
+    DG_CUDA(cudaMemcpyAsync(h_sc + first, sc.p + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+}
+
+double Stepper::energy_at(const double* x_dev) {
+    launch_energy(mesh, x_dev, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st);
+    fetch_scalars(SC_E, 1);
+    return h_sc[SC_E];
+}
+
+void Stepper::gradient_at(const double* x_dev, double* g_dev) { launch_gradient(mesh, x_dev, xt.p, cfg.dt * cfg.dt, g_dev, st); }
+
+void Stepper::refresh() {
+    launch_elem_hessians(mesh, x.p, cfg.dt * cfg.dt, true, st);
+    launch_fill(fill, mesh.He.p, a_all.p, st);
+    if (!owned.empty()) chol.factorize(a_all.p + a_off[1], st);
+}
+
+void Stepper::precondition_dev(const double* q_dev, double* p_dev) {
+    const int ndof = 3 * nV;
+    if (chol.n_total > 0) {
+        launch_gather(chol.n_total, gidx.p, q_dev, bperm.p, st);
+        chol.solve(bperm.p, xperm.p, st);
+    }
+    if (cfg.world == 1) {
+        launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, st);
+    } else {
+        launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, nullptr, p_dev, st);
+        comm->all_reduce_sum(p_dev, ndof, st);
+        k_div_dup<<<ceil_div(ndof, 256), 256, 0, st>>>(ndof, dup.p, p_dev);
+        count_launch();
+    }
+}
+
+void Stepper::frame(double* x_inout, dotgpu_frame_stats* stats) {
+    const size_t n3 = 3 * (size_t)nV;
+    const long long n = (long long)n3;
+    const double dt = cfg.dt, dtsq = dt * dt;
+    DG_CUDA(cudaEventRecord(ev[0], st));
+    std::memcpy(h_x, x_inout, n3 * sizeof(double));
+    DG_CUDA(cudaMemcpyAsync(x.p, h_x, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    hist.clear();
+    iter_log.clear();
+    int halvings = 0, evals = 0;
+    // initX(warmStart = 2)
+    launch_warm_start(nV, x.p, vel.p, mesh.fixed.p, dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
+    launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
+    ++evals;
+    gradient_at(x.p, g.p);
+    launch_dot(n, g.p, g.p, dot_partial.p, counter.p, sc.p + SC_GG, st);
+    fetch_scalars(SC_E, 2);
+    double E = h_sc[SC_E], gg = h_sc[SC_GG];
+    iter_log.insert(iter_log.end(), {0.0, E, gg});
+    int iters = 0;
+    std::vector<int> free_slots;
+    for (int i = 0; i <= cfg.history; ++i) free_slots.push_back(i);
+    do {
+        // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466) ----
+        k_neg<<<ceil_div(n, 256), 256, 0, st>>>(n, q.p, g.p);
+        count_launch();
+        for (int h = (int)hist.size() - 1; h >= 0; --h) {
+            int sl = hist[h];
+            launch_dot(n, S[sl].p, q.p, dot_partial.p, counter.p, sc.p + SC_DOT, st);
+            launch_lbfgs_first(n, q.p, Y[sl].p, sc.p, SC_DOT, SC_YS + sl, SC_KSI + sl, st);
+        }
+        precondition_dev(q.p, p.p);
+        for (int h = 0; h < (int)hist.size(); ++h) {
+            int sl = hist[h];
+            launch_dot(n, Y[sl].p, p.p, dot_partial.p, counter.p, sc.p + SC_DOT, st);
+            launch_lbfgs_second(n, p.p, S[sl].p, sc.p, SC_DOT, SC_YS + sl, SC_KSI + sl, st);
+        }
+        // ---- initial step length (Optimizer.cpp:1076-1093) ----
+        launch_dot(n, p.p, g.p, dot_partial.p, counter.p, sc.p + SC_PG, st);
+        launch_quadform(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, sc.p + SC_PHP, st);
+        fetch_scalars(SC_PG, 2);
+        double alpha = std::max(0.1, std::min(1.0, -h_sc[SC_PG] / h_sc[SC_PHP]));
+        // ---- back-tracking line search (Optimizer.cpp:752-881) ----
+        std::swap(x.p, x0.p);  // x0 = current positions
+        double Et;
+        while (true) {
+            launch_axpy(n, x.p, x0.p, p.p, alpha, st);
+            Et = energy_at(x.p);
+            ++evals;
+            if (Et > E && alpha > 0.0) {
+                alpha /= 2.0;
+                ++halvings;
+                if (alpha == 0.0) break;
+            } else
+                break;
+        }
+        E = Et;
+        // ---- history update (DOTTimeStepper.cpp:476-493) ----
+        std::swap(g.p, g_old.p);
+        gradient_at(x.p, g.p);
+        launch_dot(n, g.p, g.p, dot_partial.p, counter.p, sc.p + SC_GG, st);
+        int sl = -1;
+        if (cfg.history > 0) {
+            sl = free_slots.back();  // history+1 buffers: a candidate slot is always free
+            launch_scale_copy(n, S[sl].p, p.p, alpha, st);
+            launch_sub(n, Y[sl].p, g.p, g_old.p, st);
+            launch_dot(n, Y[sl].p, S[sl].p, dot_partial.p, counter.p, sc.p + SC_YS + sl, st);
+        }
+        fetch_scalars(0, SC_COUNT);
+        gg = h_sc[SC_GG];
+        if (sl >= 0 && h_sc[SC_YS + sl] > 0.0) {  // keep the pair iff y.s > 0, then drop the oldest beyond `history`
+            free_slots.pop_back();
+            hist.push_back(sl);
+            if ((int)hist.size() > cfg.history) {
+                free_slots.push_back(hist.front());
+                hist.pop_front();
+            }
+        }
+        ++iters;
+        iter_log.insert(iter_log.end(), {alpha, E, gg});
+    } while (gg > target && iters < cfg.max_iters);
+    DG_CUDA(cudaEventRecord(ev[1], st));
+    // ---- Hessian refresh at the end of the step (DOTTimeStepper.cpp:343, 349-380) ----
+    refresh();
+    DG_CUDA(cudaEventRecord(ev[2], st));
+    // ---- BE update (Optimizer.cpp:354-361) ----
+    launch_velocity(nV, vel.p, x.p, xn.p, dt, st);
+    DG_CUDA(cudaMemcpyAsync(xn.p, x.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    launch_xtilde(nV, xt.p, xn.p, vel.p, mesh.fixed.p, dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
+    DG_CUDA(cudaMemcpyAsync(h_x, x.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaEventRecord(ev[3], st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(x_inout, h_x, n3 * sizeof(double));
+    chol.check_status(st);
+    E_last = E;
+    if (stats) {
+        stats->iters = iters;
+        stats->halvings = halvings;
+        stats->energy_evals = evals;
+        stats->converged = gg <= target;
+        stats->E = E;
+        stats->grad_sqnorm = gg;
+        stats->target = target;
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[3]);
+        cudaEventElapsedTime(&b, ev[0], ev[1]);
+        cudaEventElapsedTime(&c, ev[1], ev[2]);
+        stats->ms_total = a;
+        stats->ms_solve = b;
+        stats->ms_refresh = c;
+    }
+}
+
+void Stepper::set_state(const double* xs, const double* velocity) {
+    const size_t n3 = 3 * (size_t)nV;
+    x.upload(xs, n3, st);
+    DG_CUDA(cudaMemcpyAsync(xn.p, x.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (velocity) vel.upload(velocity, n3, st);
+    else vel.zero(st);
+    const double dtsq = cfg.dt * cfg.dt;
+    launch_xtilde(nV, xt.p, xn.p, vel.p, mesh.fixed.p, cfg.dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
+    refresh();
+    chol.check_status(st);
+}
+
+void Stepper::get_state(double* xs, double* velocity, double* xTilde) {
+    const size_t n3 = 3 * (size_t)nV;
+    if (xs) xn.download(xs, n3, st);
+    if (velocity) vel.download(velocity, n3, st);
+    if (xTilde) xt.download(xTilde, n3, st);
+}
+
+double Stepper::time_kernels(int which, int reps) {
+    DG_REQUIRE(reps > 0, "reps must be positive");
+    const long long n = 3LL * nV;
+    cudaEvent_t a = ev[0], b = ev[1];
+    // one untimed run first
+    for (int r = -1; r < reps; ++r) {
+        if (r == 0) DG_CUDA(cudaEventRecord(a, st));
+        switch (which) {
+            case 0: launch_energy(mesh, x.p, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st); break;
+            case 1: gradient_at(x.p, g_old.p); break;
+            case 2: launch_elem_hessians(mesh, x.p, cfg.dt * cfg.dt, true, st); break;
+            case 3: launch_fill(fill, mesh.He.p, a_all.p, st); break;
+            case 4: if (!owned.empty()) chol.factorize(a_all.p + a_off[1], st); break;
+            case 5: precondition_dev(g.p, q.p); break;
+            case 6: launch_dot(n, g.p, g.p, dot_partial.p, counter.p, sc.p + SC_DOT, st); break;
+            default: throw Error(DOTGPU_ERR_INVALID, "unknown kernel id");
+        }
+    }
+    DG_CUDA(cudaEventRecord(b, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    DG_CUDA(cudaEventElapsedTime(&ms, a, b));
+    return (double)ms / reps;
+}
+
+}  // namespace dotgpu

@@ -1,0 +1,66 @@
+// Device-resident DOT time stepper (performance boundary): DOTTimeStepper::fullyImplicit /
+// solve_oneStep / updateHessianAndFactor (TimeStepper/DOTTimeStepper.cpp:273-504) and the pieces of
+// Optimizer it uses (initX, computeXTilta, lineSearch, initStepSize, the BE update of solve():
+// TimeStepper/Optimizer.cpp:327-368, 442-610, 752-881, 1076-1093) with every vector on the device.
+#pragma once
+#include <deque>
+#include <memory>
+
+#include "chol_numeric.h"
+#include "device_mesh.h"
+#include "linalg.h"
+#include "mesh_host.h"
+
+namespace dotgpu {
+
+struct Comm;  // NCCL communicator wrapper (comm.cpp)
+
+struct Stepper {
+    dotgpu_stepper_config cfg;
+    int nV = 0, nT = 0;
+    cudaStream_t st = nullptr;
+    std::vector<double> V_rest, mass_h;
+    std::vector<int32_t> tets_h, epart_h;
+    std::vector<uint8_t> fixed_h;
+    DDHost dd;
+    std::vector<int> owned;          // subdomain ids handled by this rank, ascending
+    std::vector<int64_t> a_off;      // value offsets: [0]=global, [1+i]=owned[i]
+    DeviceMesh mesh;
+    DevBuf<double> a_all;
+    DevBuf<int> g_ia, g_ja;
+    DeviceFill fill;
+    CholBatch chol;
+    DevBuf<int> gidx, cptr, cidx, dup;
+    DevBuf<double> x, x0, xn, xt, vel, g, g_old, q, p, bperm, xperm, qf_partial, dot_partial;
+    std::vector<DevBuf<double>> S, Y;
+    std::deque<int> hist;            // slots, oldest first
+    DevBuf<double> sc;               // device scalars
+    DevBuf<unsigned> counter;
+    double* h_sc = nullptr;          // pinned mirror
+    double* h_x = nullptr;           // pinned staging for positions
+    double target = 0.0;
+    double E_last = 0.0;
+    std::vector<double> iter_log;    // (alpha, E, |g|^2) rows
+    int64_t launches0 = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::unique_ptr<Comm> comm;
+    DevBuf<unsigned char> own_tet;   // multi-GPU: 1 if this rank sums the tet into energy/gradient
+
+    ~Stepper();
+    void create(const dotgpu_stepper_config& c, int nV, int nT, const double* V_rest, const int32_t* tets, const int32_t* epart,
+                const uint8_t* fixed_mask);
+    void frame(double* x_inout, dotgpu_frame_stats* stats);
+    void set_state(const double* x, const double* velocity);
+    void get_state(double* x, double* velocity, double* xTilde);
+    void precondition_dev(const double* q_dev, double* p_dev);
+    void refresh();  // elemental Hessians at x, matrix fill, numeric factorisation
+    double energy_at(const double* x_dev);
+    void gradient_at(const double* x_dev, double* g_dev);
+    void fetch_scalars(int first, int count);
+    double compute_target() const;
+    double time_kernels(int which, int reps);
+};
+
+enum ScalarSlot { SC_E = 0, SC_GG = 1, SC_PG = 2, SC_PHP = 3, SC_DOT = 4, SC_YS = 8, SC_KSI = 24, SC_COUNT = 48 };
+
+}  // namespace dotgpu

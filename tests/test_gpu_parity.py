@@ -1,0 +1,306 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI (libdotgpu via
+ctypes) and is compared with (a) golden vectors produced by the unmodified reference and (b) the pinned
+CPU oracle on the same inputs.  Tolerances follow SURVEY.md section 8(c) and are stated at each check."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import dot_b200 as D
+from dot_b200 import meshgen
+from golden_util import Golden, rel
+from oracle import dot_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RUN_CASES = ["tiny_snh_k4_twist", "tiny_fcr_k4_twistnsns", "small_snh_k4_twist", "small_fcr_k3_stretch", "small_snh_k5_tsns_dt24"]
+KERNEL_CASES = ["tiny_fcr_inverted", "tiny_snh_inverted", "small_fcr_perturbed"]
+
+
+def _energy(g):
+    V, T = g["setup/V_rest"], g["setup/F"]
+    fm = np.zeros(V.shape[0], dtype=np.uint8)
+    fm[g["setup/fixed"]] = 1
+    return D.Energy(g.meta["energy"], T, g["setup/restTriInv"], g["setup/triArea"], g["setup/mu"], g["setup/lambda"], V.shape[0], fm)
+
+
+@pytest.mark.parametrize("name", RUN_CASES + KERNEL_CASES)
+def test_energy_gradient_svd_hessian_vs_reference(name):
+    g = Golden(name)
+    en, dt = g.meta["energy"], g.meta["dt"]
+    e = _energy(g)
+    m = O.Mesh(g["setup/V_rest"], g["setup/F"])
+    for st in g.states():
+        x = g[st + "/V"]
+        fm = np.zeros(m.nV, dtype=np.uint8)
+        fm[g[st + "/fixed"]] = 1
+        e.set_fixed(fm)
+        # a2/a3: F bit-for-bit up to fp contraction (1e-15), singular values to 1e-11 abs (reference SVD noise)
+        F, U, S, V = e.svd(x)
+        assert rel(F, g[st + "/F"]) < 1e-14
+        assert np.abs(S - g[st + "/Sigma"]).max() < 1e-11
+        assert np.abs(np.einsum("tia,ta,tja->tij", U, S, V) - F).max() < 1e-13
+        assert np.abs(U @ np.swapaxes(U, 1, 2) - np.eye(3)).max() < 1e-13
+        assert np.abs(V @ np.swapaxes(V, 1, 2) - np.eye(3)).max() < 1e-13
+        assert (np.linalg.det(U) > 0).all() and (np.linalg.det(V) > 0).all()
+        assert (np.abs(S[:, 0]) >= np.abs(S[:, 1]) - 1e-14).all() and (np.abs(S[:, 1]) >= np.abs(S[:, 2]) - 1e-14).all()
+        assert np.array_equal(S[:, 2] < 0, g[st + "/Sigma"][:, 2] < 0)
+        # a5: per-element energies 1e-11 rel; total 1e-11
+        assert rel(e.energy_per_elem(x), g[st + "/E_per_elem"]) < 1e-11
+        Eel = e.compute_energy_val(x, dt * dt)
+        assert abs(Eel - g[st + "/E"][1]) <= 1e-11 * abs(g[st + "/E"][1])
+        # a6/a7: gradient; 2e-8 vs the reference dump (its own SVD noise, see tests/test_oracle_golden.py),
+        # 1e-12 vs the oracle's closed-form/SVD route on the same input
+        gel = e.compute_gradient(x, dt * dt)
+        assert rel(gel, g[st + "/g_elastic"]) < 2e-8
+        Uo, So, Vo = O.svd_rot(O.deformation_gradient(m, x))
+        Po = O.first_piola(en, Uo, So, Vo, m.mu, m.lam)
+        go = O.gather_gradient(m, O.elem_gradient(m, Po, dt * dt), fm.astype(bool))
+        assert rel(gel, go) < 1e-12
+        assert np.all(gel.reshape(-1, 3)[fm.astype(bool)] == 0.0)
+        # a8: elemental projected Hessians 1e-8 vs the reference (clamping sees slightly different sigma), 1e-10 vs oracle
+        He, vi = e.compute_elem_hessians(x, dt * dt, True)
+        Href = g[st + "/He"]
+        n = Href.shape[0]
+        assert rel(He[:n], Href) < 1e-8
+        assert rel((He ** 2).sum(axis=(1, 2)), g[st + "/He_sqnorm"]) < 1e-8
+        Ho = O.elem_hessians(en, m, Uo, So, Vo, dt * dt, True)
+        assert rel(He, Ho) < 1e-10
+        assert np.abs(He - np.swapaxes(He, 1, 2)).max() <= 1e-13 * np.abs(He).max()
+        T = g["setup/F"]
+        assert np.array_equal(vi, np.where(fm[T] > 0, -T - 1, T))
+        # unprojected Hessian = true second derivative
+        Hn, _ = e.compute_elem_hessians(x, dt * dt, False)
+        assert rel(Hn, O.elem_hessians(en, m, Uo, So, Vo, dt * dt, False)) < 1e-10
+
+
+def test_svd_edge_cases():
+    """identity, zero, rank-1, rank-2, reflections, huge/small scales, repeated singular values"""
+    rng = np.random.default_rng(3)
+    Fs = [np.eye(3), np.zeros((3, 3)), np.outer([1, 2, 3], [1, 1, 0.0]), np.diag([2.0, 1.0, 0.0]), np.diag([1.0, 1.0, -1.0]),
+          np.diag([2.0, 2.0, 2.0]), 1e-9 * rng.standard_normal((3, 3)), 1e9 * rng.standard_normal((3, 3)), -np.eye(3),
+          np.eye(3) + 1e-16 * rng.standard_normal((3, 3))]
+    Fs += [np.eye(3) + 0.8 * rng.standard_normal((3, 3)) for _ in range(200)]
+    Fs = np.asarray(Fs)
+    n = Fs.shape[0]
+    # one tet per matrix: rest shape = unit tet, x = F X
+    X = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    V = np.concatenate([X + 10.0 * i for i in range(n)])
+    T = np.arange(4 * n, dtype=np.int32).reshape(n, 4)
+    Dm, vol, mass, mu, lam = D.mesh_features(V, T)
+    e = D.Energy("FCR", T, Dm, vol, mu, lam, 4 * n)
+    x = np.concatenate([X @ Fs[i].T + 10.0 * i for i in range(n)])
+    F, U, S, Vv = e.svd(x)
+    scale = np.maximum(np.abs(Fs).max(axis=(1, 2)), 1e-300)[:, None, None]
+    assert (np.abs(F - Fs) / np.maximum(scale, 1e-9) < 1e-6).all()     # F itself carries the +10*i translation rounding
+    assert (np.abs(np.einsum("tia,ta,tja->tij", U, S, Vv) - F) / np.maximum(np.abs(F).max(axis=(1, 2)), 1e-300)[:, None, None] < 1e-13).all()
+    assert np.abs(U @ np.swapaxes(U, 1, 2) - np.eye(3)).max() < 1e-13
+    assert (np.linalg.det(U) > 0.999).all() and (np.linalg.det(Vv) > 0.999).all()
+    sl = np.linalg.svd(F, compute_uv=False)
+    assert (np.abs(np.abs(S) - sl) <= 1e-13 * np.maximum(sl[:, :1], 1e-300)).all()
+    assert np.array_equal(S[0], [1.0, 1.0, 1.0]) and np.array_equal(S[9], [1.0, 1.0, 1.0])   # identity stays exact
+
+
+@pytest.mark.parametrize("name,sub", [("tiny_snh_k4_twist", 0), ("tiny_snh_k4_twist", 3), ("small_snh_k4_twist", 1),
+                                      ("small_fcr_k3_stretch", 2), ("small_snh_k5_tsns_dt24", 4), ("small_snh_k4_twist", -1)])
+def test_solver_factor_solve_multiply(name, sub):
+    """a11: LinSysSolver boundary on the reference's own matrices (values dumped from CHOLMODSolver::a)."""
+    g = Golden(name)
+    st = g.states()[-1]
+    pre = "global_" if sub < 0 else "sbd%d_" % sub
+    ia, ja, a = g["setup/" + pre + "ia"], g["setup/" + pre + "ja"], g[st + "/" + pre + "a"]
+    s = D.Solver(ia, ja)
+    s.set_values(a)
+    s.factorize()
+    A = O.csr_upper_to_full(ia, ja, a)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        b = rng.standard_normal(s.n)
+        x = s.solve(b)
+        # relative residual <= 1e-12, solution vs SuperLU 1e-9
+        assert np.linalg.norm(A @ x - b) <= 1e-12 * (np.linalg.norm(b) + abs(A).sum(axis=1).max() * np.linalg.norm(x))
+        assert rel(x, spla.spsolve(A, b)) < 1e-9
+        assert rel(s.multiply(b), A @ b) < 1e-14
+    if sub >= 0:
+        # the reference's own solve of -g restricted to the subdomain
+        m = O.Mesh(g["setup/V_rest"], g["setup/F"])
+        l2g = g["setup/sbd%d_l2g" % sub]
+        rhs = (-g[st + "/g"]).reshape(-1, 3)[l2g].reshape(-1)
+        assert rel(s.solve(rhs), g[st + "/sbd%d_p" % sub]) < 1e-9
+    # refactorisation with new values reuses the analysis
+    s.set_values(2.0 * a)
+    s.factorize()
+    assert rel(s.solve(b), 0.5 * x) < 1e-12
+
+
+def test_solver_reports_indefinite_matrix():
+    g = Golden("tiny_snh_k4_twist")
+    ia, ja, a = g["setup/sbd0_ia"], g["setup/sbd0_ja"], g["frame6/sbd0_a"].copy()
+    s = D.Solver(ia, ja)
+    a[ia[30]] = -1.0  # a negative diagonal entry
+    s.set_values(a)
+    with pytest.raises(D.DotGpuError) as e:
+        s.factorize()
+    assert e.value.code == -4
+    with pytest.raises(D.DotGpuError):
+        D.Solver(ia, ja).solve(np.zeros(len(ia) - 1))  # solve before factorize
+
+
+def _stepper(g, **kw):
+    V, T = g["setup/V_rest"], g["setup/F"]
+    a = D.Anim(g.meta["anim"], V)
+    return D.Stepper(V, T, g["setup/epart"], a.fixed_mask(), energy=g.meta["energy"], k=g.k, dt=g.meta["dt"], **kw), a
+
+
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_stepper_matrices_and_preconditioner_vs_reference(name):
+    """a9/a10: global + subdomain matrices after a Hessian refresh at the reference's state; a11/a12: one
+    application of the decomposed preconditioner; a13: E, g, p.Hp of the incremental potential."""
+    g = Golden(name)
+    stp, anim = _stepper(g)
+    assert abs(stp.target - g.meta["stats"]["targetGRes"]) <= 1e-12 * stp.target
+    for st in g.states():
+        stp.set_state(g[st + "/V"], g[st + "/velocity"])
+        xs, vs, xt = stp.get_state()
+        assert np.abs(xt - g[st + "/xTilta"]).max() < 1e-15
+        assert rel(stp.matrix(-1), g[st + "/global_a"]) < 1e-8
+        for s in range(g.k):
+            assert rel(stp.matrix(s), g[st + "/sbd%d_a" % s]) < 1e-8, s
+        E, gr = stp.eval(g[st + "/V"])
+        assert abs(E - g[st + "/E"][0]) <= 1e-11 * abs(E)
+        assert rel(gr, g[st + "/g"]) < 2e-8
+        p = stp.precondition(-g[st + "/g"])
+        assert rel(p, g[st + "/p"]) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["tiny_snh_k4_twist", "tiny_fcr_k4_twistnsns"])
+def test_stepper_follows_reference_from_restart(name):
+    """a12/a13: exact iteration path from the reference's state after its first dumped frame (same iteration
+    counts, same step sizes, positions to 1e-8).  Frame 1 is excluded for the reason given in
+    tests/test_oracle_golden.py::test_time_stepping_follows_reference_from_restart."""
+    g = Golden(name)
+    stp, anim = _stepper(g)
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    x = g["setup/V_rest"].copy()
+    for _ in range(f0):
+        anim.step(x, g.meta["dt"])          # replay the scripted handle motion
+    stp.set_state(g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    x = g["frame%d/V" % f0].copy()
+    ref_stats = g.iter_stats()
+    for f in range(f0 + 1, dumps[-1] + 1):
+        anim.step(x, g.meta["dt"])
+        fs = stp.frame(x)
+        ref = ref_stats[ref_stats[:, 0] == f - 1]
+        log = stp.iter_log()
+        assert fs.iters == g.meta["stats"]["frame_iters"][f - 1], f
+        assert fs.converged == 1
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-5, atol=0)
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-5)
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-4)
+        if g.has("frame%d/V" % f):
+            assert np.abs(x - g["frame%d/V" % f]).max() < 1e-8, f
+            _, v, _ = stp.get_state()
+            assert np.abs(v - g["frame%d/velocity" % f]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_stepper_from_rest_converges_like_reference(name):
+    g = Golden(name)
+    stp, anim = _stepper(g)
+    x = g["setup/V_rest"].copy()
+    for f in range(1, g.meta["frames"] + 1):
+        anim.step(x, g.meta["dt"])
+        fs = stp.frame(x)
+        assert fs.converged == 1 and fs.grad_sqnorm <= fs.target
+        assert abs(fs.iters - g.meta["stats"]["frame_iters"][f - 1]) <= 4
+        if g.has("frame%d/V" % f):
+            # both converged to the same minimiser within the solver tolerance (iteration paths may differ in frame 1)
+            assert np.abs(x - g["frame%d/V" % f]).max() < 5e-4, f
+
+
+def test_stepper_vs_oracle_on_a_larger_bar():
+    """bar2K (5,184 tets), SNH, 6 subdomains by slabs (labels need not come from METIS for this check): the
+    device stepper and the CPU oracle run the same frames from rest."""
+    V, T = meshgen.preset("bar2K")
+    V = meshgen.normalise_like_loader(V)
+    cx = V[T].mean(axis=1)[:, 0]
+    epart = np.minimum((cx * 6).astype(np.int32), 5)
+    m = O.Mesh(V, T)
+    ref = O.DOTStepper(m, "SNH", epart, "twist", 0.025)
+    a = D.Anim("twist", V)
+    stp = D.Stepper(V, T, epart, a.fixed_mask(), energy="SNH", k=6)
+    assert abs(stp.target - ref.target) <= 1e-12 * ref.target
+    x = V.copy()
+    for f in range(3):
+        a.step(x, 0.025)
+        fs = stp.frame(x)
+        it = ref.step_frame()
+        assert fs.converged == 1
+        assert abs(fs.iters - it) <= 2
+        assert np.abs(x - ref.x).max() < 2e-5
+        if fs.iters == it:
+            log, rl = stp.iter_log(), np.asarray(ref.log)[-(it + 1):]
+            assert np.allclose(log[:, 1], rl[:, 1], rtol=1e-9)
+
+
+def test_full_size_properties_bar17k():
+    """BASELINE config C2 size (86,400 tets, METIS labels from the reference): size-independent properties."""
+    import os
+    V, T = meshgen.preset("bar17K_like")
+    V = meshgen.normalise_like_loader(V)
+    ep = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels_bar17K_like_k8.npz"))["epart"].astype(np.int32)
+    a = D.Anim("twist", V)
+    fm = a.fixed_mask()
+    stp = D.Stepper(V, T, ep, fm, energy="SNH", k=8)
+    nV = V.shape[0]
+    # rest state: gradient of the elastic part vanishes (SNH rest stress is zero), energy = sum vol * lam/2 (mu/lam)^2 * dt^2
+    E0, g0 = stp.eval(V)
+    Dm, vol, mass, mu, lam = D.mesh_features(V, T)
+    xt = stp.get_state()[2]
+    Ein = (((V - xt) ** 2).sum(axis=1) * mass / 2).sum()
+    assert abs(E0 - (0.025 ** 2 * (vol * lam / 2 * (mu / lam) ** 2).sum() + Ein)) <= 1e-10 * E0
+    # gradient is translation invariant in its elastic part: sum over free+fixed of elemental forces = 0 -> checked via
+    # a rigid translation leaving the elastic gradient unchanged
+    e = D.Energy("SNH", T, Dm, vol, mu, lam, nV, np.zeros(nV, dtype=np.uint8))
+    rng = np.random.default_rng(0)
+    xr = V + 0.01 * rng.standard_normal(V.shape)
+    g1 = e.compute_gradient(xr, 1.0)
+    g2 = e.compute_gradient(xr + np.array([0.3, -0.2, 0.1]), 1.0)
+    assert rel(g2, g1) < 1e-10
+    assert np.abs(g1.reshape(-1, 3).sum(axis=0)).max() < 1e-8 * np.abs(g1).max() * np.sqrt(nV)
+    # rotation invariance of the energy
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    R = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1.0]])
+    assert abs(e.compute_energy_val(xr @ R.T) - e.compute_energy_val(xr)) <= 1e-11 * abs(e.compute_energy_val(xr))
+    # finite-difference check of the gradient along a random direction
+    d = rng.standard_normal(V.shape)
+    h = 1e-6
+    fd = (e.compute_energy_val(xr + h * d) - e.compute_energy_val(xr - h * d)) / (2 * h)
+    assert abs(fd - g1 @ d.reshape(-1)) <= 1e-6 * abs(fd)
+    # preconditioner: symmetric positive definite operator, fixed dofs map to zero, linear
+    q1, q2 = rng.standard_normal(3 * nV), rng.standard_normal(3 * nV)
+    q1.reshape(-1, 3)[fm > 0] = 0
+    q2.reshape(-1, 3)[fm > 0] = 0
+    p1, p2 = stp.precondition(q1), stp.precondition(q2)
+    assert abs(p1 @ q2 - p2 @ q1) <= 1e-9 * abs(p1 @ q2)
+    assert p1 @ q1 > 0
+    assert rel(stp.precondition(q1 + 2 * q2), p1 + 2 * p2) < 1e-10
+    assert np.all(p1.reshape(-1, 3)[fm > 0] == 0)
+    # subdomain matrices are SPD and solve to residual 1e-12 through the stand-alone solver boundary
+    dd = stp.dd()
+    ia, ja = dd.pattern(3)
+    a3 = stp.matrix(3)
+    A = O.csr_upper_to_full(ia, ja, a3)
+    s = D.Solver(ia, ja)
+    s.set_values(a3)
+    s.factorize()
+    b = rng.standard_normal(s.n)
+    xs = s.solve(b)
+    assert np.linalg.norm(A @ xs - b) <= 1e-12 * (np.linalg.norm(b) + abs(A).sum(axis=1).max() * np.linalg.norm(xs))
+    # a few frames converge
+    x = V.copy()
+    for f in range(3):
+        a.step(x, 0.025)
+        fs = stp.frame(x)
+        assert fs.converged == 1 and fs.iters < 60
+    assert np.isfinite(x).all()
