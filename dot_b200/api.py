@@ -326,6 +326,14 @@ class Stepper:
         _chk(lib().dotgpu_stepper_frame(self.h, _p(x), C.byref(st)))
         return st
 
+    def frame_resident(self, fixed_idx, fixed_pos):
+        """Positions stay on the device; only the scripted Dirichlet targets (ids + positions) are passed."""
+        idx = _i32(fixed_idx)
+        pos = _f64(fixed_pos)
+        st = FrameStats()
+        _chk(lib().dotgpu_stepper_frame_resident(self.h, _p(idx), _p(pos), idx.shape[0], C.byref(st)))
+        return st
+
     def set_state(self, x, velocity=None):
         _chk(lib().dotgpu_stepper_set_state(self.h, _p(_f64(x)), _p(_f64(velocity)) if velocity is not None else None))
 

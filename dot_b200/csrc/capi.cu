@@ -470,6 +470,14 @@ int dotgpu_stepper_frame(dotgpu_stepper* s, double* x_inout, dotgpu_frame_stats*
     s->s.frame(x_inout, stats);
     API_END
 }
+int dotgpu_stepper_frame_resident(dotgpu_stepper* s, const int32_t* fixed_idx, const double* fixed_pos, int count,
+                                  dotgpu_frame_stats* stats) {
+    API_BEGIN
+    DG_REQUIRE(s, "null argument");
+    DG_CUDA(cudaSetDevice(s->s.cfg.device));
+    s->s.frame_resident(fixed_idx, fixed_pos, count, stats);
+    API_END
+}
 int dotgpu_stepper_set_state(dotgpu_stepper* s, const double* x, const double* velocity) {
     API_BEGIN
     DG_REQUIRE(s && x, "null argument");

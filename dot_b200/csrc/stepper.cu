@@ -15,6 +15,14 @@ __global__ void k_div_dup(int ndof, const int* __restrict__ dup, double* __restr
     int du = dup[d / 3];
     if (du > 1) p[d] /= (double)du;
 }
+__global__ void k_set_rows(int count, const int* __restrict__ idx, const double* __restrict__ pos, double* __restrict__ x) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int v = idx[i];
+    x[3 * (size_t)v] = pos[3 * i];
+    x[3 * (size_t)v + 1] = pos[3 * i + 1];
+    x[3 * (size_t)v + 2] = pos[3 * i + 2];
+}
 __global__ void k_neg(long long n, double* __restrict__ out, const double* __restrict__ in) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = -in[i];
@@ -267,11 +275,34 @@ void Stepper::precondition_dev(const double* q_dev, double* p_dev) {
 
 void Stepper::frame(double* x_inout, dotgpu_frame_stats* stats) {
     const size_t n3 = 3 * (size_t)nV;
-    const long long n = (long long)n3;
-    const double dt = cfg.dt, dtsq = dt * dt;
     DG_CUDA(cudaEventRecord(ev[0], st));
     std::memcpy(h_x, x_inout, n3 * sizeof(double));
     DG_CUDA(cudaMemcpyAsync(x.p, h_x, n3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    frame_core(stats, true);
+    std::memcpy(x_inout, h_x, n3 * sizeof(double));
+}
+
+void Stepper::frame_resident(const int32_t* idx, const double* pos, int count, dotgpu_frame_stats* stats) {
+    const size_t n3 = 3 * (size_t)nV;
+    DG_REQUIRE(count >= 0 && (count == 0 || (idx && pos)), "bad Dirichlet target list");
+    for (int i = 0; i < count; ++i) DG_REQUIRE(idx[i] >= 0 && idx[i] < nV, "Dirichlet vertex out of range");
+    DG_CUDA(cudaEventRecord(ev[0], st));
+    // x = x^n (resident) with the scripted rows overwritten
+    DG_CUDA(cudaMemcpyAsync(x.p, xn.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (count > 0) {
+        if (h_idx.n < (size_t)count) { h_idx.alloc(count); h_pos.alloc(3 * (size_t)count); }
+        DG_CUDA(cudaMemcpyAsync(h_idx.p, idx, count * sizeof(int), cudaMemcpyHostToDevice, st));
+        DG_CUDA(cudaMemcpyAsync(h_pos.p, pos, 3 * (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_set_rows<<<ceil_div(count, 128), 128, 0, st>>>(count, h_idx.p, h_pos.p, x.p);
+        count_launch();
+    }
+    frame_core(stats, false);
+}
+
+void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
+    const size_t n3 = 3 * (size_t)nV;
+    const long long n = (long long)n3;
+    const double dt = cfg.dt, dtsq = dt * dt;
     hist.clear();
     iter_log.clear();
     int halvings = 0, evals = 0;
@@ -354,10 +385,9 @@ void Stepper::frame(double* x_inout, dotgpu_frame_stats* stats) {
     launch_velocity(nV, vel.p, x.p, xn.p, dt, st);
     DG_CUDA(cudaMemcpyAsync(xn.p, x.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     launch_xtilde(nV, xt.p, xn.p, vel.p, mesh.fixed.p, dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
-    DG_CUDA(cudaMemcpyAsync(h_x, x.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (copy_back) DG_CUDA(cudaMemcpyAsync(h_x, x.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaEventRecord(ev[3], st));
     DG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(x_inout, h_x, n3 * sizeof(double));
     chol.check_status(st);
     E_last = E;
     if (stats) {

@@ -50,6 +50,10 @@ struct Stepper {
     void create(const dotgpu_stepper_config& c, int nV, int nT, const double* V_rest, const int32_t* tets, const int32_t* epart,
                 const uint8_t* fixed_mask);
     void frame(double* x_inout, dotgpu_frame_stats* stats);
+    void frame_resident(const int32_t* idx, const double* pos, int count, dotgpu_frame_stats* stats);
+    void frame_core(dotgpu_frame_stats* stats, bool copy_back);
+    DevBuf<int> h_idx;
+    DevBuf<double> h_pos;
     void set_state(const double* x, const double* velocity);
     void get_state(double* x, double* velocity, double* xTilde);
     void precondition_dev(const double* q_dev, double* p_dev);

@@ -194,6 +194,11 @@ void dotgpu_stepper_destroy(dotgpu_stepper* s);
  * x_inout [nV*3] host: on entry x^n with the scripted Dirichlet move applied (what result.V holds after
  * stepAnimScript), on return the converged positions. */
 int dotgpu_stepper_frame(dotgpu_stepper* s, double* x_inout, dotgpu_frame_stats* stats);
+/* Same time step with the positions already resident on the device (they are: the stepper keeps x^n): only the
+ * scripted Dirichlet targets travel, as `count` vertex ids + positions [count*3] (host).  Nothing is copied back;
+ * read the result with dotgpu_stepper_get_state. */
+int dotgpu_stepper_frame_resident(dotgpu_stepper* s, const int32_t* fixed_idx, const double* fixed_pos, int count,
+                                  dotgpu_frame_stats* stats);
 /* restart (Optimizer ctor :126-177 reading `status<n>`): positions + velocity; refreshes the Hessians at x. */
 int dotgpu_stepper_set_state(dotgpu_stepper* s, const double* x, const double* velocity);
 int dotgpu_stepper_get_state(dotgpu_stepper* s, double* x, double* velocity, double* xTilde);
