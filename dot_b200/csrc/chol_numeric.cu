@@ -8,8 +8,10 @@
 // Factorisation of one level: extend-add children CBs -> for every pivot tile kb: potrf(tile) + tile
 // inverse, trsm of the rows below (a GEMM with the tile inverse), rank-64 update of the whole trailing
 // front (rest of the panel + CB).  GEMM tiles are 64x64 per CTA on DMMA (mma.sync m8n8k4 f64).
-// Solves: per level fwd_top (block forward substitution with the tile inverses), fwd_below (update
-// vectors, gathered deterministically by the parent), and the mirror image going down.
+// After the numeric factorisation the "solve panels" S_s = [L_ss^-1 ; -L_below L_ss^-1] are built (batched over
+// all supernodes), so that each level of a triangular solve is ONE launch of independent dense GEMV slabs:
+// forward [y_s; u_s] = S_s (b_s + children updates) with the children gathered deterministically by the parent,
+// backward x_s = S_s^T [y_s; x(rows below)].
 #include <algorithm>
 
 #include "chol_numeric.h"
@@ -272,138 +274,211 @@ __global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks,
             }
 }
 
-// ---- forward solve, top part: y_s = L_ss^-1 (b_s + children updates) ----
-__global__ void __launch_bounds__(256) k_fwd_top(const int* __restrict__ tasks, const SNDesc* __restrict__ sn,
-                                                 const long long* __restrict__ ea_ptr, const long long* __restrict__ ea_src,
-                                                 const double* __restrict__ L, const double* __restrict__ tinv,
-                                                 const double* __restrict__ b, const double* __restrict__ uwork,
-                                                 double* __restrict__ y) {
-    extern __shared__ double smem[];
-    const SNDesc d = sn[tasks[blockIdx.x]];
-    double* t = smem;            // [ns]
-    double* tmp = smem + d.ns;   // [64]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < d.ns; k += 256) {
-        double v = b[d.col0 + k];
-        for (long long e = ea_ptr[d.rows + k]; e < ea_ptr[d.rows + k + 1]; ++e) v += uwork[ea_src[e]];
-        t[k] = v;
-    }
-    __syncthreads();
-    const double* __restrict__ P = L + d.panel;
-    for (int c0 = 0; c0 < d.ns; c0 += NB) {
-        const int w = min(NB, d.ns - c0);
-        // tmp[r] = t[c0+r] - L[c0+r, 0:c0] . x[0:c0]     (x overwrites t)
-        for (int r = warp; r < w; r += 8) {
-            const double* __restrict__ row = P + (long long)(c0 + r) * d.ns;
-            double sum = 0.0;
-            for (int k = lane; k < c0; k += 32) sum += row[k] * t[k];
+// ---- solve panels:  S_s = [ L_ss^-1 ; -L_below L_ss^-1 ]  (m x ns, row-major, same offsets as the L panels) ----
+// With S every phase of a triangular solve is a dense GEMV that any number of CTAs can share: there is no serial
+// substitution chain left inside a supernode ("hard parts": sparse triangular solves).
+constexpr int TLD = 72;  // smem leading dimension of a [KC][64] operand chunk given as B[k][n]
+
+// sB[k][n] = (k < kw && n < ncols) ? src[k*ld + n] : 0   for k < KC, n < 64;  128 threads
+__device__ __forceinline__ void load_chunk_kn(double* sB, const double* __restrict__ src, long long ld, int kw, int ncols) {
+    const int n = threadIdx.x & 63, k0 = threadIdx.x >> 6;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-            if (lane == 0) tmp[r] = t[c0 + r] - sum;
-        }
-        __syncthreads();
-        const double* __restrict__ D = tinv + d.tinv + (long long)(c0 / NB) * NB * NB;
-        for (int r = warp; r < w; r += 8) {
-            double sum = 0.0;
-            for (int k = lane; k <= r; k += 32) sum += D[r * NB + k] * tmp[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-            if (lane == 0) t[c0 + r] = sum;
-        }
-        __syncthreads();
+    for (int i = 0; i < 16; ++i) {
+        int k = k0 + 2 * i;
+        double v = 0.0;
+        if (k < kw && n < ncols) v = src[(long long)k * ld + n];
+        sB[k * TLD + n] = v;
     }
-    for (int k = threadIdx.x; k < d.ns; k += 256) y[d.col0 + k] = t[k];
 }
 
-// ---- forward solve, below part: u_s = (children updates) - L_below y_s ----
-__global__ void __launch_bounds__(256) k_fwd_below(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
-                                                   const long long* __restrict__ ea_ptr, const long long* __restrict__ ea_src,
-                                                   const double* __restrict__ L, const double* __restrict__ y,
-                                                   double* __restrict__ uwork) {
+// acc += A_chunk[64 x KC] * B_chunk[KC x 64] with B stored [k][n]
+__device__ __forceinline__ void mma_chunk_kn(double (&acc)[4][4][2], const double* sA, const double* sB, int wr, int wc, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int k0 = 0; k0 < KC; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[(wr * 32 + i * 8 + g) * SLD + k0 + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = sB[(k0 + q) * TLD + wc * 32 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+// diagonal tiles of L_ss^-1 are the tile inverses
+__global__ void __launch_bounds__(256) k_sp_diag(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                 const double* __restrict__ tinv, double* __restrict__ Sp) {
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int c0 = tk.a * NB, w = min(NB, d.ns - c0);
+    const double* __restrict__ D = tinv + d.tinv + (long long)tk.a * NB * NB;
+    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+        int r = e >> 6, c = e & 63;
+        if (r < w && c < w) Sp[d.panel + (long long)(c0 + r) * d.ns + c0 + c] = D[e];
+    }
+}
+
+// block row i of X = L_ss^-1:  X_ij = -D_i * sum_{k=j}^{i-1} L_ik X_kj   (j < i); one CTA per (s, j)
+__global__ void __launch_bounds__(128) k_sp_triinv(const Task2* __restrict__ tasks, int i, const SNDesc* __restrict__ sn,
+                                                   const double* __restrict__ L, const double* __restrict__ tinv,
+                                                   double* __restrict__ Sp) {
+    __shared__ double sA[64 * SLD], sB[KC * TLD];
+    const Task2 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int j = tk.a;
+    const int r0 = i * NB, c0 = j * NB;
+    const int wi = min(NB, d.ns - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    const int g = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // acc = sum_k L_ik X_kj, K runs over columns c0 .. r0-1 of block row i
+    const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns;
+    const double* __restrict__ X = Sp + d.panel;
+    for (int k0 = c0; k0 < r0; k0 += KC) {
+        __syncthreads();
+        load_chunk(sA, A + k0, d.ns, wi, r0 - k0);
+        load_chunk_kn(sB, X + (long long)k0 * d.ns + c0, d.ns, r0 - k0, NB);
+        __syncthreads();
+        mma_chunk_kn(acc, sA, sB, wr, wc, lane);
+    }
+    // out = -D_i * acc : feed acc back through shared memory as the [k][n] operand, 32 rows at a time
+    double out[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) out[a][b][0] = out[a][b][1] = 0.0;
+    const double* __restrict__ D = tinv + d.tinv + (long long)i * NB * NB;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();
+        if (wr == half) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) sB[(a * 8 + g) * TLD + wc * 32 + b * 8 + 2 * q + e] = acc[a][b][e];
+        }
+        load_chunk(sA, D + half * KC, NB, NB, KC);
+        __syncthreads();
+        mma_chunk_kn(out, sA, sB, wr, wc, lane);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int r = wr * 32 + a * 8 + g, c = wc * 32 + b * 8 + 2 * q + e;
+                if (r < wi) Sp[d.panel + (long long)(r0 + r) * d.ns + c0 + c] = -out[a][b][e];
+            }
+}
+
+// below part: S[ns+r][c] = -sum_{k >= c-tile} L_below[r][k] X[k][c]; one CTA per (s, 64-row slab, column tile)
+__global__ void __launch_bounds__(128) k_sp_below(const Task3* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                  const double* __restrict__ L, double* __restrict__ Sp) {
+    __shared__ double sA[64 * SLD], sB[KC * TLD];
+    const Task3 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int r0 = d.ns + tk.a * 64, c0 = tk.b * NB;
+    const int nrows = min(64, d.m - r0), ncols = min(NB, d.ns - c0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    const int g = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns;
+    const double* __restrict__ X = Sp + d.panel;
+    for (int k0 = c0; k0 < d.ns; k0 += KC) {
+        __syncthreads();
+        load_chunk(sA, A + k0, d.ns, nrows, d.ns - k0);
+        load_chunk_kn(sB, X + (long long)k0 * d.ns + c0, d.ns, d.ns - k0, ncols);
+        __syncthreads();
+        mma_chunk_kn(acc, sA, sB, wr, wc, lane);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int r = wr * 32 + a * 8 + g, c = wc * 32 + b * 8 + 2 * q + e;
+                if (r < nrows && c < ncols) Sp[d.panel + (long long)(r0 + r) * d.ns + c0 + c] = -acc[a][b][e];
+            }
+}
+
+// ---- forward sweep of one level: [y_s ; u_s] = S_s t (+ children updates), t = b_s + children updates ----
+__global__ void __launch_bounds__(256) k_fwd(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                             const long long* __restrict__ ea_ptr, const long long* __restrict__ ea_src,
+                                             const double* __restrict__ Sp, const double* __restrict__ b,
+                                             double* __restrict__ uwork, double* __restrict__ y) {
     extern __shared__ double smem[];
     const Task2 tk = tasks[blockIdx.x];
     const SNDesc d = sn[tk.s];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < d.ns; k += 256) smem[k] = y[d.col0 + k];
+    const int r0 = tk.a * 64, r1 = min(r0 + 64, d.m);
+    // t is needed up to column min(r1, ns) only (rows of the triangular top part stop at their diagonal)
+    const int tn = min(d.ns, r1);
+    for (int k = threadIdx.x; k < tn; k += 256) {
+        double v = b[d.col0 + k];
+        for (long long e = ea_ptr[d.rows + k]; e < ea_ptr[d.rows + k + 1]; ++e) v += uwork[ea_src[e]];
+        smem[k] = v;
+    }
     __syncthreads();
-    const int nb = d.m - d.ns;
-    const int i0 = tk.a * 64, i1 = min(i0 + 64, nb);
-    for (int i = i0 + warp; i < i1; i += 8) {
-        const double* __restrict__ row = L + d.panel + (long long)(d.ns + i) * d.ns;
+    for (int r = r0 + warp; r < r1; r += 8) {
+        const double* __restrict__ row = Sp + d.panel + (long long)r * d.ns;
+        const int kn = r < d.ns ? r + 1 : d.ns;
         double sum = 0.0;
-        for (int k = lane; k < d.ns; k += 32) sum += row[k] * smem[k];
+        for (int k = lane; k < kn; k += 32) sum += row[k] * smem[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
         if (lane == 0) {
-            double v = 0.0;
-            const long long gr = d.rows + d.ns + i;
-            for (long long e = ea_ptr[gr]; e < ea_ptr[gr + 1]; ++e) v += uwork[ea_src[e]];
-            uwork[d.u + i] = v - sum;
+            if (r < d.ns) {
+                y[d.col0 + r] = sum;
+            } else {
+                double v = 0.0;
+                for (long long e = ea_ptr[d.rows + r]; e < ea_ptr[d.rows + r + 1]; ++e) v += uwork[ea_src[e]];
+                uwork[d.u + (r - d.ns)] = v + sum;
+            }
         }
     }
 }
 
-// ---- backward solve, below part: r_s[c] = sum_i L_below[i][c] x[rows_below[i]]  (64-column slab per CTA) ----
-__global__ void __launch_bounds__(256) k_bwd_below(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
-                                                   const int* __restrict__ rows, const double* __restrict__ L,
-                                                   const double* __restrict__ x, double* __restrict__ rwork) {
+// ---- backward sweep of one level: x_s = S_s^T [y_s ; x(rows below)]  (64-column slab per CTA) ----
+__global__ void __launch_bounds__(256) k_bwd(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                             const int* __restrict__ rows, const double* __restrict__ Sp,
+                                             const double* __restrict__ y, double* __restrict__ x) {
+    extern __shared__ double smem[];  // z[m]
     __shared__ double red[4][64];
     const Task2 tk = tasks[blockIdx.x];
     const SNDesc d = sn[tk.s];
-    const int c = tk.a * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
-    const int nb = d.m - d.ns;
+    const int c0 = tk.a * 64;
+    const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int c = c0 + cl;
+    // rows above the slab's first column contribute nothing (upper triangle)
+    for (int r = c0 + threadIdx.x; r < d.m; r += 256) smem[r] = r < d.ns ? y[d.col0 + r] : x[rows[d.rows + r]];
+    __syncthreads();
     double sum = 0.0;
     if (c < d.ns) {
-        const int* __restrict__ rb = rows + d.rows + d.ns;
-        const double* __restrict__ P = L + d.panel + (long long)d.ns * d.ns + c;
-        for (int i = grp; i < nb; i += 4) sum += P[(long long)i * d.ns] * x[rb[i]];
+        const double* __restrict__ col = Sp + d.panel + c;
+        // diagonal tile: rows c0 .. c0+63 need the r >= c mask
+        const int dend = min(c0 + 64, d.ns);
+        for (int r = c0 + grp; r < dend; r += 4)
+            if (r >= c) sum += col[(long long)r * d.ns] * smem[r];
+        for (int r = dend + grp; r < d.m; r += 4) sum += col[(long long)r * d.ns] * smem[r];
     }
-    red[grp][threadIdx.x & 63] = sum;
+    red[grp][cl] = sum;
     __syncthreads();
-    if (grp == 0 && c < d.ns) rwork[d.col0 + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
-}
-
-// ---- backward solve, top part: x_s = L_ss^-T (y_s - r_s) ----
-__global__ void __launch_bounds__(256) k_bwd_top(const int* __restrict__ tasks, const SNDesc* __restrict__ sn,
-                                                 const double* __restrict__ L, const double* __restrict__ tinv,
-                                                 const double* __restrict__ y, const double* __restrict__ rwork,
-                                                 double* __restrict__ x) {
-    extern __shared__ double smem[];
-    __shared__ double red[4][64];
-    const SNDesc d = sn[tasks[blockIdx.x]];
-    double* z = smem;           // [ns] -> solution
-    double* tmp = smem + d.ns;  // [64]
-    const bool has_below = d.m > d.ns;
-    for (int k = threadIdx.x; k < d.ns; k += 256) z[k] = y[d.col0 + k] - (has_below ? rwork[d.col0 + k] : 0.0);
-    __syncthreads();
-    const double* __restrict__ P = L + d.panel;
-    const int nblk = (d.ns + NB - 1) / NB;
-    const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    for (int jb = nblk - 1; jb >= 0; --jb) {
-        const int c0 = jb * NB;
-        const int w = min(NB, d.ns - c0);
-        // tmp[c] = z[c0+c] - sum_{k >= c0+w} L[k][c0+c] x[k]
-        double sum = 0.0;
-        if (cl < w) {
-            const double* __restrict__ col = P + c0 + cl;
-            for (int k = c0 + w + grp; k < d.ns; k += 4) sum += col[(long long)k * d.ns] * z[k];
-        }
-        red[grp][cl] = sum;
-        __syncthreads();
-        if (grp == 0 && cl < w) tmp[cl] = z[c0 + cl] - ((red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]));
-        __syncthreads();
-        // x[c] = sum_{k >= c} D[k][c] tmp[k]
-        const double* __restrict__ D = tinv + d.tinv + (long long)jb * NB * NB;
-        sum = 0.0;
-        if (cl < w)
-            for (int k = cl + grp; k < w; k += 4) sum += D[k * NB + cl] * tmp[k];
-        __syncthreads();
-        red[grp][cl] = sum;
-        __syncthreads();
-        if (grp == 0 && cl < w) z[c0 + cl] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
-        __syncthreads();
-    }
-    for (int k = threadIdx.x; k < d.ns; k += 256) x[d.col0 + k] = z[k];
+    if (grp == 0 && c < d.ns) x[d.col0 + c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
 }
 
 }  // namespace
@@ -519,19 +594,36 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
                 }
             P.update[kb].cnt = ((int)tasks.size() - P.update[kb].off) / 2;
         }
-        P.fwd_top.off = (int)tasks.size();
-        for (int s : sns) tasks.push_back(s);
-        P.fwd_top.cnt = (int)sns.size();
-        P.bwd_top = P.fwd_top;
-        P.fwd_below.off = (int)tasks.size();
+        P.fwd.off = (int)tasks.size();
         for (int s : sns)
-            for (int a = 0; a * 64 < sn[s].m - sn[s].ns; ++a) push2(s, a);
-        P.fwd_below.cnt = ((int)tasks.size() - P.fwd_below.off) / 2;
-        P.bwd_below.off = (int)tasks.size();
+            for (int a = 0; a * 64 < sn[s].m; ++a) push2(s, a);
+        P.fwd.cnt = ((int)tasks.size() - P.fwd.off) / 2;
+        P.bwd.off = (int)tasks.size();
         for (int s : sns)
-            if (sn[s].m > sn[s].ns)
-                for (int a = 0; a * 64 < sn[s].ns; ++a) push2(s, a);
-        P.bwd_below.cnt = ((int)tasks.size() - P.bwd_below.off) / 2;
+            for (int a = 0; a * 64 < sn[s].ns; ++a) push2(s, a);
+        P.bwd.cnt = ((int)tasks.size() - P.bwd.off) / 2;
+    }
+    // solve-panel construction (independent of the elimination tree: batched over all supernodes)
+    {
+        int max_nblk = 0;
+        for (int s = 0; s < nsuper_total; ++s) max_nblk = std::max(max_nblk, (sn[s].ns + NB - 1) / NB);
+        sp_diag.off = (int)tasks.size();
+        for (int s = 0; s < nsuper_total; ++s)
+            for (int a = 0; a * NB < sn[s].ns; ++a) push2(s, a);
+        sp_diag.cnt = ((int)tasks.size() - sp_diag.off) / 2;
+        sp_triinv.assign(max_nblk, Span());
+        for (int i = 1; i < max_nblk; ++i) {
+            sp_triinv[i].off = (int)tasks.size();
+            for (int s = 0; s < nsuper_total; ++s)
+                if (i * NB < sn[s].ns)
+                    for (int j = 0; j < i; ++j) push2(s, j);
+            sp_triinv[i].cnt = ((int)tasks.size() - sp_triinv[i].off) / 2;
+        }
+        sp_below.off = (int)tasks.size();
+        for (int s = 0; s < nsuper_total; ++s)
+            for (int a = 0; a * 64 < sn[s].m - sn[s].ns; ++a)
+                for (int b = 0; b * NB < sn[s].ns; ++b) push2(s, (a & 0xffff) | (b << 16));
+        sp_below.cnt = ((int)tasks.size() - sp_below.off) / 2;
     }
     if (tasks.empty()) tasks.push_back(0);
 
@@ -546,6 +638,7 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     d_ea_src.upload(ea_src, st);
     d_tasks.upload(tasks, st);
     L.alloc(std::max<int64_t>(nnz_l_total, 1));
+    Sp.alloc(std::max<int64_t>(nnz_l_total, 1));
     CB.alloc(std::max<int64_t>(cb_total, 1));
     tinv.alloc(std::max<int64_t>(tinv_total, 1));
     ywork.alloc(n_total);
@@ -554,20 +647,19 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     uwork.alloc(std::max<int64_t>(u_total, 1));
     d_status.alloc(1);
     d_status.zero(st);
-    int max_ns = 0;
-    for (auto& S : sym) max_ns = std::max(max_ns, S.max_nscol);
-    size_t shm_top = (size_t)(max_ns + 64) * sizeof(double);
-    DG_REQUIRE(shm_top <= 200 * 1024, "supernode too wide for the solve kernels' shared memory");
+    max_front_all = 0;
+    for (auto& S : sym) max_front_all = std::max(max_front_all, S.max_front);
+    const size_t shm_solve = (size_t)(max_front_all + 8) * sizeof(double);
+    DG_REQUIRE(shm_solve <= 200 * 1024, "front too large for the solve kernels' shared memory");
     DG_CUDA(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(k_fwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
-    DG_CUDA(cudaFuncSetAttribute(k_bwd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
-    DG_CUDA(cudaFuncSetAttribute(k_fwd_below, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_top, 1024)));
+    DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_solve, 1024)));
+    DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_solve, 1024)));
     DG_CUDA(cudaStreamSynchronize(st));
     factorized = false;
 }
 
 int64_t CholBatch::device_bytes() const {
-    return (int64_t)(L.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
+    return (int64_t)(L.bytes() + Sp.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
                      d_amap.bytes() + d_ea_ptr.bytes() + d_ea_src.bytes() + d_tasks.bytes() + d_sn.bytes());
 }
 
@@ -602,6 +694,20 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
             }
         }
     }
+    // ---- solve panels ----
+    if (sp_diag.cnt) {
+        k_sp_diag<<<sp_diag.cnt, 256, 0, st>>>((const Task2*)(T + sp_diag.off), d_sn.p, tinv.p, Sp.p);
+        count_launch();
+    }
+    for (size_t i = 1; i < sp_triinv.size(); ++i)
+        if (sp_triinv[i].cnt) {
+            k_sp_triinv<<<sp_triinv[i].cnt, 128, 0, st>>>((const Task2*)(T + sp_triinv[i].off), (int)i, d_sn.p, L.p, tinv.p, Sp.p);
+            count_launch();
+        }
+    if (sp_below.cnt) {
+        k_sp_below<<<sp_below.cnt, 128, 0, st>>>((const Task3*)(T + sp_below.off), d_sn.p, L.p, Sp.p);
+        count_launch();
+    }
     factorized = true;
 }
 
@@ -615,30 +721,18 @@ void CholBatch::check_status(cudaStream_t st) {
 void CholBatch::solve(const double* b_perm, double* x_perm, cudaStream_t st) {
     if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
     const int* T = d_tasks.p;
-    int max_ns = 0;
-    for (auto& S : sym) max_ns = std::max(max_ns, S.max_nscol);
-    const size_t shm = (size_t)(max_ns + 64) * sizeof(double);
+    const size_t shm = (size_t)(max_front_all + 8) * sizeof(double);
     for (int lv = 0; lv < nlevels; ++lv) {
         const LevelPlan& P = plan[lv];
-        if (P.fwd_top.cnt) {
-            k_fwd_top<<<P.fwd_top.cnt, 256, shm, st>>>(T + P.fwd_top.off, d_sn.p, d_ea_ptr.p, d_ea_src.p, L.p, tinv.p, b_perm, uwork.p,
-                                                       ywork.p);
-            count_launch();
-        }
-        if (P.fwd_below.cnt) {
-            k_fwd_below<<<P.fwd_below.cnt, 256, shm, st>>>((const Task2*)(T + P.fwd_below.off), d_sn.p, d_ea_ptr.p, d_ea_src.p, L.p,
-                                                           ywork.p, uwork.p);
+        if (P.fwd.cnt) {
+            k_fwd<<<P.fwd.cnt, 256, shm, st>>>((const Task2*)(T + P.fwd.off), d_sn.p, d_ea_ptr.p, d_ea_src.p, Sp.p, b_perm, uwork.p, ywork.p);
             count_launch();
         }
     }
     for (int lv = nlevels - 1; lv >= 0; --lv) {
         const LevelPlan& P = plan[lv];
-        if (P.bwd_below.cnt) {
-            k_bwd_below<<<P.bwd_below.cnt, 256, 0, st>>>((const Task2*)(T + P.bwd_below.off), d_sn.p, d_rows.p, L.p, xwork.p, rwork.p);
-            count_launch();
-        }
-        if (P.bwd_top.cnt) {
-            k_bwd_top<<<P.bwd_top.cnt, 256, shm, st>>>(T + P.bwd_top.off, d_sn.p, L.p, tinv.p, ywork.p, rwork.p, xwork.p);
+        if (P.bwd.cnt) {
+            k_bwd<<<P.bwd.cnt, 256, shm, st>>>((const Task2*)(T + P.bwd.off), d_sn.p, d_rows.p, Sp.p, ywork.p, xwork.p);
             count_launch();
         }
     }

@@ -32,16 +32,19 @@ struct CholBatch {
     DevBuf<SNDesc> d_sn;
     DevBuf<int> d_rows, d_rel, d_child;
     DevBuf<long long> d_amap, d_ea_ptr, d_ea_src;
-    DevBuf<double> L, CB, tinv, ywork, xwork, uwork, rwork;
+    DevBuf<double> L, Sp, CB, tinv, ywork, xwork, uwork, rwork;
     DevBuf<int> d_status;
     DevBuf<int> d_tasks;
 
     struct Span { int off = 0, cnt = 0; };
     struct LevelPlan {
-        Span extend, fwd_top, fwd_below, bwd_below, bwd_top;
+        Span extend, fwd, bwd;
         std::vector<Span> potrf, trsm, update;  // per pivot step
     };
     std::vector<LevelPlan> plan;
+    Span sp_diag, sp_below;
+    std::vector<Span> sp_triinv;
+    int max_front_all = 0;
     bool factorized = false;
 
     // ia/ja per matrix: CSR upper patterns.  Builds symbolic + device structures.
