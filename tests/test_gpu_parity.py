@@ -97,7 +97,8 @@ def test_svd_edge_cases():
     assert (np.linalg.det(U) > 0.999).all() and (np.linalg.det(Vv) > 0.999).all()
     sl = np.linalg.svd(F, compute_uv=False)
     assert (np.abs(np.abs(S) - sl) <= 1e-13 * np.maximum(sl[:, :1], 1e-300)).all()
-    assert np.array_equal(S[0], [1.0, 1.0, 1.0]) and np.array_equal(S[9], [1.0, 1.0, 1.0])   # identity stays exact
+    assert np.array_equal(S[0], [1.0, 1.0, 1.0])          # identity stays exact (matters for the rest-state Hessian)
+    assert np.abs(S[9] - 1.0).max() <= 4.5e-16
 
 
 @pytest.mark.parametrize("name,sub", [("tiny_snh_k4_twist", 0), ("tiny_snh_k4_twist", 3), ("small_snh_k4_twist", 1),
@@ -219,8 +220,9 @@ def test_stepper_from_rest_converges_like_reference(name):
 
 
 def test_stepper_vs_oracle_on_a_larger_bar():
-    """bar2K (5,184 tets), SNH, 6 subdomains by slabs (labels need not come from METIS for this check): the
-    device stepper and the CPU oracle run the same frames from rest."""
+    """bar2K (5,184 tets), SNH, 6 subdomains by slabs (labels need not come from METIS for this check): the device
+    stepper follows the CPU oracle iteration by iteration from the oracle's state after frame 1 (frame 1 itself is
+    compared at solver tolerance: its preconditioner is the degenerate rest-state Hessian)."""
     V, T = meshgen.preset("bar2K")
     V = meshgen.normalise_like_loader(V)
     cx = V[T].mean(axis=1)[:, 0]
@@ -231,16 +233,24 @@ def test_stepper_vs_oracle_on_a_larger_bar():
     stp = D.Stepper(V, T, epart, a.fixed_mask(), energy="SNH", k=6)
     assert abs(stp.target - ref.target) <= 1e-12 * ref.target
     x = V.copy()
+    a.step(x, 0.025)
+    fs = stp.frame(x)
+    it = ref.step_frame()
+    assert fs.converged == 1 and abs(fs.iters - it) <= 3
+    assert np.abs(x - ref.x).max() < 5e-4
+    stp.set_state(ref.x, ref.vel)
+    x = ref.x.copy()
     for f in range(3):
         a.step(x, 0.025)
         fs = stp.frame(x)
+        ref.log = []
         it = ref.step_frame()
-        assert fs.converged == 1
-        assert abs(fs.iters - it) <= 2
-        assert np.abs(x - ref.x).max() < 2e-5
-        if fs.iters == it:
-            log, rl = stp.iter_log(), np.asarray(ref.log)[-(it + 1):]
-            assert np.allclose(log[:, 1], rl[:, 1], rtol=1e-9)
+        assert fs.converged == 1 and fs.iters == it
+        log, rl = stp.iter_log(), np.asarray(ref.log)
+        assert np.allclose(log[:, 0], rl[:, 0], rtol=1e-9)       # step sizes
+        assert np.allclose(log[:, 1], rl[:, 1], rtol=1e-11)      # energies
+        assert np.allclose(log[:, 2], rl[:, 2], rtol=1e-6)       # |g|^2
+        assert np.abs(x - ref.x).max() < 1e-9
 
 
 def test_full_size_properties_bar17k():
@@ -282,8 +292,10 @@ def test_full_size_properties_bar17k():
     q1.reshape(-1, 3)[fm > 0] = 0
     q2.reshape(-1, 3)[fm > 0] = 0
     p1, p2 = stp.precondition(q1), stp.precondition(q2)
-    assert abs(p1 @ q2 - p2 @ q1) <= 1e-9 * abs(p1 @ q2)
-    assert p1 @ q1 > 0
+    # p = D^-1 A q with A = sum_s R^T H_s^-1 R symmetric positive definite and D = diag(dup): D p is the symmetric part
+    dupw = np.repeat(stp.dd().dup().astype(float), 3)
+    assert abs((dupw * p1) @ q2 - (dupw * p2) @ q1) <= 1e-9 * abs((dupw * p1) @ q2)
+    assert (dupw * p1) @ q1 > 0
     assert rel(stp.precondition(q1 + 2 * q2), p1 + 2 * p2) < 1e-10
     assert np.all(p1.reshape(-1, 3)[fm > 0] == 0)
     # subdomain matrices are SPD and solve to residual 1e-12 through the stand-alone solver boundary
