@@ -652,8 +652,10 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     const size_t shm_solve = (size_t)(max_front_all + 8) * sizeof(double);
     DG_REQUIRE(shm_solve <= 200 * 1024, "front too large for the solve kernels' shared memory");
     DG_CUDA(cudaFuncSetAttribute(k_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_solve, 1024)));
-    DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(shm_solve, 1024)));
+    // the opt-in limit is a per-function, process-wide attribute shared by every CholBatch: always raise it to the cap
+    // (a smaller batch analysed later must not lower it under a larger one; occupancy follows the launch-time size)
+    DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaStreamSynchronize(st));
     factorized = false;
 }
@@ -715,6 +717,7 @@ void CholBatch::check_status(cudaStream_t st) {
     int h = 0;
     DG_CUDA(cudaMemcpyAsync(&h, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(cudaGetLastError());
     if (h != 0) throw Error(DOTGPU_ERR_NOT_SPD, "matrix not positive definite (supernode " + std::to_string(h - 1) + ")");
 }
 

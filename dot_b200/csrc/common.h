@@ -72,6 +72,7 @@ struct DevBuf {
     void download(T* h, size_t cnt, cudaStream_t st = 0) const {
         if (cnt) DG_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
         DG_CUDA(cudaStreamSynchronize(st));
+        DG_CUDA(cudaGetLastError());  // a kernel launch rejected earlier on this thread must not pass silently
     }
     void zero(cudaStream_t st = 0) {
         if (n) DG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));

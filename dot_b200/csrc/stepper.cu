@@ -241,6 +241,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
 void Stepper::fetch_scalars(int first, int count) {
     DG_CUDA(cudaMemcpyAsync(h_sc + first, sc.p + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
     DG_CUDA(cudaStreamSynchronize(st));
+    DG_CUDA(cudaGetLastError());
 }
 
 double Stepper::energy_at(const double* x_dev) {
