@@ -284,10 +284,9 @@ int dotgpu_solver_solve(dotgpu_solver* s, const double* rhs, double* x) {
     DG_CUDA(cudaSetDevice(s->device));
     const int n = s->n;
     s->tmp.upload(rhs, n, s->st);
-    k_permute_in<<<ceil_div(n, 256), 256, 0, s->st>>>(n, s->d_perm.p, s->tmp.p, s->b.p);
-    s->chol.solve(s->b.p, s->x.p, s->st);
+    s->chol.solve(s->tmp.p, s->d_perm.p, s->x.p, s->st);
     k_permute_out<<<ceil_div(n, 256), 256, 0, s->st>>>(n, s->d_perm.p, s->x.p, s->tmp.p);
-    count_launch(2);
+    count_launch(1);
     s->tmp.download(x, n, s->st);
     API_END
 }

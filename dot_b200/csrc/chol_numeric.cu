@@ -656,12 +656,13 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     // (a smaller batch analysed later must not lower it under a larger one; occupancy follows the launch-time size)
     DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    build_solve_plan(sn, st);
     DG_CUDA(cudaStreamSynchronize(st));
     factorized = false;
 }
 
 int64_t CholBatch::device_bytes() const {
-    return (int64_t)(L.bytes() + Sp.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
+    return (int64_t)(Pf.bytes() + Pb.bytes() + d_ell.bytes() + d_stasks.bytes() + L.bytes() + Sp.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
                      d_amap.bytes() + d_ea_ptr.bytes() + d_ea_src.bytes() + d_tasks.bytes() + d_sn.bytes());
 }
 
@@ -710,6 +711,7 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
         k_sp_below<<<sp_below.cnt, 128, 0, st>>>((const Task3*)(T + sp_below.off), d_sn.p, L.p, Sp.p);
         count_launch();
     }
+    pack_panels(st);
     factorized = true;
 }
 
@@ -721,7 +723,7 @@ void CholBatch::check_status(cudaStream_t st) {
     if (h != 0) throw Error(DOTGPU_ERR_NOT_SPD, "matrix not positive definite (supernode " + std::to_string(h - 1) + ")");
 }
 
-void CholBatch::solve(const double* b_perm, double* x_perm, cudaStream_t st) {
+void CholBatch::solve_levels(const double* b_perm, double* x_perm, cudaStream_t st) {
     if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
     const int* T = d_tasks.p;
     const size_t shm = (size_t)(max_front_all + 8) * sizeof(double);

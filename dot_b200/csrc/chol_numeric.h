@@ -18,6 +18,19 @@ struct SNDesc {
     int m, ns, col0, child_begin, child_end, parent;
 };
 
+// streamed solve (chol_solve.cu): per-supernode descriptor and task (one contiguous byte range of a packed panel)
+struct SolveSN {
+    long long pf, pb;   // offsets (doubles) of the packed forward / backward panels (same size, 128-byte aligned)
+    long long u, rows, ell;
+    int m, ns, col0, parent, nchild, child_begin, ntask_f, ntask_b;
+};
+struct SolveTask {
+    long long src;      // 16-byte aligned offset (doubles) into Pf (kind 0) or Pb (kind 1)
+    int s, r0, r1;      // supernode, row range (forward: front rows, backward: columns)
+    int ndbl, shift;    // doubles to stream, position of row r0 inside the streamed range
+    int kind;
+};
+
 struct CholBatch {
     int nmat = 0;
     std::vector<Symbolic> sym;            // host symbolic per matrix
@@ -46,6 +59,17 @@ struct CholBatch {
     std::vector<Span> sp_triinv;
     int max_front_all = 0;
     bool factorized = false;
+    // streamed solve
+    DevBuf<SolveSN> d_ssn;
+    DevBuf<SolveTask> d_stasks;
+    DevBuf<int> d_ell, d_ptasks;
+    DevBuf<double> Pf, Pb;
+    DevBuf<unsigned long long> d_cnt;
+    int64_t pk_total = 0;
+    int n_solve_tasks = 0, n_pack_tasks = 0, stage_dbl = 0, solve_grid = 0;
+    size_t solve_smem = 0;
+    void build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st);
+    void pack_panels(cudaStream_t st);
 
     // ia/ja per matrix: CSR upper patterns.  Builds symbolic + device structures.
     void analyze(const std::vector<const int32_t*>& ia, const std::vector<const int32_t*>& ja, const std::vector<int>& n,
@@ -54,9 +78,13 @@ struct CholBatch {
     void factorize(const double* a_all, cudaStream_t st);
     // throws Error(DOTGPU_ERR_NOT_SPD) if the last factorize met a non-positive pivot (syncs the stream)
     void check_status(cudaStream_t st);
-    // b_perm / x_perm: device vectors of n_total doubles in the PERMUTED order of each matrix
-    // (b_perm[col_off[m] + i] = b_m[perm_m[i]]); in place allowed (b_perm == x_perm)
-    void solve(const double* b_perm, double* x_perm, cudaStream_t st);
+    // x_perm: device vector of n_total doubles in the PERMUTED order of each matrix (x_perm[col_off[m] + i] = x_m[perm_m[i]]).
+    // Right-hand side: entry i of the permuted concatenation is b[gidx[i]] (gather fused into the solve), or b[i] when
+    // gidx == nullptr (then b is already permuted and b == x_perm is allowed).
+    void solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st);
+    // level-by-level reference implementation of the same solve (one launch per level and direction); kept as the
+    // in-library cross-check of the streamed kernel
+    void solve_levels(const double* b_perm, double* x_perm, cudaStream_t st);
     int64_t device_bytes() const;
 };
 

@@ -261,8 +261,7 @@ void Stepper::refresh() {
 void Stepper::precondition_dev(const double* q_dev, double* p_dev) {
     const int ndof = 3 * nV;
     if (chol.n_total > 0) {
-        launch_gather(chol.n_total, gidx.p, q_dev, bperm.p, st);
-        chol.solve(bperm.p, xperm.p, st);
+        chol.solve(q_dev, gidx.p, xperm.p, st);  // right-hand-side gather fused into the streamed solve
     }
     if (cfg.world == 1) {
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, st);
