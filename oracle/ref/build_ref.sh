@@ -79,4 +79,28 @@ printf '%s\n' "$S/Energy/Energy.cpp" "$S/Energy/Physics_Elasticity/FixedCoRotEne
 
 g++ -fopenmp "$OBJ"/dot/*.o "$OUT/libsuitesparse_dot.a" "$OUT/libmetis.a" "$BLASLIB" -Wl,--disable-new-dtags -Wl,-rpath,"$BLASDIR" -lpthread -lm -o "$OUT/dot_ref"
 echo "$BLASDIR" > "$OUT/blasdir.txt"
+
+# ---------- drop-in build: the SAME unmodified reference steppers over libdotgpu (integration/dropin) ----------
+# integration/dropin precedes src/LinSysSolver on the include path, so every `#include "CHOLMODSolver.hpp"` of the
+# reference resolves to the libdotgpu-backed class; CHOLMODSolver.cpp is not compiled.  Needs dot_b200/libdotgpu.so.
+REPO="$(cd "$HERE/../.." && pwd)"
+if [ -f "$REPO/dot_b200/libdotgpu.so" ]; then
+  mkdir -p "$OBJ/dot_gpu"
+  GINC="-I$REPO/integration/dropin -I$REPO/include $INC"
+  dotgpu_cc() {
+    local src="$1"
+    local o="$OBJ/dot_gpu/$(basename "${src%.cpp}").o"
+    [ "$o" -nt "$src" ] && [ "$o" -nt "$REPO/integration/dropin/CHOLMODSolver.hpp" ] && [ "$o" -nt "$REPO/integration/dropin/GpuEnergy.hpp" ] \
+      || g++ $CXXF -DDOTGPU_DROPIN $GINC -c "$src" -o "$o"
+  }
+  export -f dotgpu_cc; export GINC REPO
+  printf '%s\n' "$S/Energy/Energy.cpp" "$S/Energy/Physics_Elasticity/FixedCoRotEnergy.cpp" "$S/Energy/Physics_Elasticity/StableNHEnergy.cpp" \
+    "$S/Mesh.cpp" "$S/Config.cpp" "$S/AnimScripter.cpp" "$S/Utils/IglUtils.cpp" \
+    "$S/TimeStepper/Optimizer.cpp" "$S/TimeStepper/ADMMDDTimeStepper.cpp" "$S/TimeStepper/DOTTimeStepper.cpp" \
+    "$S/Utils/SVD_EFTYCHIOS/Singular_Value_Decomposition_Helper.cpp" "$S/Utils/SVD_EFTYCHIOS/PTHREAD_QUEUE.cpp" \
+    "$HERE/driver.cpp" | xargs -P "$JOBS" -I{} bash -c 'dotgpu_cc {}'
+  g++ -fopenmp "$OBJ"/dot_gpu/*.o "$OUT/libmetis.a" -L"$REPO/dot_b200" -ldotgpu -Wl,--disable-new-dtags \
+    -Wl,-rpath,'$ORIGIN/../../dot_b200' -lpthread -lm -o "$OUT/dot_ref_gpu"
+  echo "build_ref: built $OUT/dot_ref_gpu (reference steppers over libdotgpu)"
+fi
 echo "build_ref: built $OUT/dot_ref (BLAS: $BLASLIB)"

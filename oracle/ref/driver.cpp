@@ -28,6 +28,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <omp.h>
+#include <mutex>
 
 #define protected public
 #define private public
@@ -44,6 +45,11 @@
 #include "Timer.hpp"
 #undef protected
 #undef private
+#ifdef DOTGPU_DROPIN
+// drop-in build (oracle/_ref/dot_ref_gpu): the same unmodified reference steppers, but "CHOLMODSolver.hpp" above resolved to
+// integration/dropin/CHOLMODSolver.hpp (libdotgpu-backed LinSysSolver) and the energy object is GpuEnergy<reference energy>.
+#include "GpuEnergy.hpp"
+#endif
 
 // ---- globals the reference translation units expect (main.cpp:27-88) ----
 DOT::Config config;  // global => zero-initialised enums
@@ -295,7 +301,7 @@ int main(int argc, char** argv)
     int parts = -1, frames = 10, threads = 0;
     long heCap = -1;
     double tol = -1, dtOverride = -1;
-    bool quiet = false, labelsOnly = false;
+    bool quiet = false, labelsOnly = false, cpuEnergy = false;
     std::set<int> dumpFrames;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -312,6 +318,7 @@ int main(int argc, char** argv)
         else if (a == "--threads") threads = std::stoi(next());
         else if (a == "--quiet") quiet = true;
         else if (a == "--labels-only") labelsOnly = true;
+        else if (a == "--cpu-energy") cpuEnergy = true;  // drop-in build only: keep the reference's CPU energy, GPU solvers only
         else if (a == "--dump-dir") dumpDir = next();
         else if (a == "--he-cap") heCap = std::stol(next());
         else if (a == "--kernel-state") kernelState = next();
@@ -409,10 +416,19 @@ int main(int argc, char** argv)
     std::vector<DOT::Energy<DIM>*> energyTerms;
     std::vector<double> energyParams;
     energyParams.emplace_back(1.0);
+#ifdef DOTGPU_DROPIN
+    if (!cpuEnergy) {
+        switch (config.energyType) {
+            case DOT::ET_SNH: energyTerms.emplace_back(new DOT::GpuEnergy<DOT::StableNHEnergy<DIM>>(DOTGPU_ENERGY_SNH)); break;
+            case DOT::ET_FCR: energyTerms.emplace_back(new DOT::GpuEnergy<DOT::FixedCoRotEnergy<DIM>>(DOTGPU_ENERGY_FCR)); break;
+        }
+    } else
+#endif
     switch (config.energyType) {
         case DOT::ET_SNH: energyTerms.emplace_back(new DOT::StableNHEnergy<DIM>()); break;
         case DOT::ET_FCR: energyTerms.emplace_back(new DOT::FixedCoRotEnergy<DIM>()); break;
     }
+    (void)cpuEnergy;
     auto t0 = std::chrono::steady_clock::now();
     Opt* opt = nullptr;
     DotOpt* dot = nullptr;

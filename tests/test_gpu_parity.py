@@ -316,3 +316,48 @@ def test_full_size_properties_bar17k():
         fs = stp.frame(x)
         assert fs.converged == 1 and fs.iters < 60
     assert np.isfinite(x).all()
+
+
+def _run_ref_binary(exe, tmp, script, frames, extra=()):
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="4")
+    blas = os.path.join(root, "oracle", "_ref", "blasdir.txt")
+    if os.path.exists(blas):
+        env["LD_LIBRARY_PATH"] = open(blas).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    dump = os.path.join(tmp, "dump_" + os.path.basename(exe))
+    out = subprocess.run([exe, "--script", script, "--frames", str(frames), "--quiet", "--threads", "4", "--dump-dir", dump,
+                          "--dump-frames", str(frames), "--he-cap", "8"] + list(extra), cwd=tmp, env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    st = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    return st, np.load(os.path.join(dump, "frame%d" % frames, "V.npy"))
+
+
+@pytest.mark.parametrize("energy,k,tol", [("SNH", 4, 1e-9), ("FCR", 3, 1e-9)])
+def test_dropin_unmodified_reference_steppers_over_libdotgpu(tmp_path, energy, k, tol):
+    """Row (b): the reference's own DOTTimeStepper / Optimizer, compiled unmodified, run with
+    integration/dropin/CHOLMODSolver.hpp (every LinSysSolver -> libdotgpu) and GpuEnergy<reference energy>
+    (computeEnergyVal / computeGradient / computeElemHessianByPK -> libdotgpu), against the all-CPU reference binary
+    on the same script.  Same METIS labels (both call the vendored METIS), tol 1e-9: positions agree to 1e-6 of the
+    bounding box per SURVEY 8(c) (measured: ~1e-9); iteration counts may differ by a few (different factor ordering)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cpu, gpu = os.path.join(root, "oracle", "_ref", "dot_ref"), os.path.join(root, "oracle", "_ref", "dot_ref_gpu")
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
+    V, T = meshgen.preset("bar_small")
+    msh, script = str(tmp_path / "mesh.msh"), str(tmp_path / "script.txt")
+    meshgen.write_msh(msh, V, T)
+    meshgen.write_script(script, msh, energy=energy, parts=k, anim="twist", dt=0.025)
+    frames = 4
+    st_c, x_c = _run_ref_binary(cpu, str(tmp_path), script, frames, ["--tol", str(tol)])
+    st_g, x_g = _run_ref_binary(gpu, str(tmp_path), script, frames, ["--tol", str(tol)])
+    bbox = (x_c.max(axis=0) - x_c.min(axis=0)).max()
+    assert np.abs(x_g - x_c).max() <= 1e-6 * bbox
+    assert abs(st_g["inner_iters"] - st_c["inner_iters"]) <= max(3, 0.1 * st_c["inner_iters"])
+    # solvers only (reference CPU energy + libdotgpu factor/solve): isolates the LinSysSolver boundary
+    st_s, x_s = _run_ref_binary(gpu, str(tmp_path), script, frames, ["--tol", str(tol), "--cpu-energy"])
+    assert np.abs(x_s - x_c).max() <= 1e-6 * bbox
