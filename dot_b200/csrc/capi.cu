@@ -310,7 +310,12 @@ static void fill_info(const Symbolic& S, int64_t nnz_a, int64_t bytes, dotgpu_so
     info->max_front = S.max_front;
     info->max_nscol = S.max_nscol;
     info->nnz_a = nnz_a;
-    info->nnz_l = S.nnz_l;
+    // nnz(L) of the supernodal factor: dense lower-triangular diagonal blocks + dense sub-diagonal blocks (what the solves stream)
+    info->nnz_l = 0;
+    for (int k = 0; k < S.nsuper; ++k) {
+        const int64_t ns = S.nscol(k), m = S.front(k);
+        info->nnz_l += ns * (ns + 1) / 2 + (m - ns) * ns;
+    }
     info->flops = S.flops;
     info->device_bytes = bytes;
 }

@@ -488,8 +488,17 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
                         int leaf_nodes, cudaStream_t st) {
     nmat = (int)n.size();
     sym.assign(nmat, Symbolic());
+    std::string first_error;  // exceptions must not leave an OpenMP region
 #pragma omp parallel for schedule(dynamic)
-    for (int m = 0; m < nmat; ++m) sym[m].analyze(n[m], ia[m], ja[m], leaf_nodes);
+    for (int m = 0; m < nmat; ++m) {
+        try {
+            sym[m].analyze(n[m], ia[m], ja[m], leaf_nodes);
+        } catch (const std::exception& e) {
+#pragma omp critical
+            if (first_error.empty()) first_error = e.what();
+        }
+    }
+    if (!first_error.empty()) throw Error(DOTGPU_ERR_INVALID, first_error);
     col_off.assign(nmat + 1, 0);
     nnz_off.assign(nmat + 1, 0);
     sn_off.assign(nmat + 1, 0);
@@ -662,7 +671,7 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
 }
 
 int64_t CholBatch::device_bytes() const {
-    return (int64_t)(Pf.bytes() + Pb.bytes() + d_ell.bytes() + d_stasks.bytes() + L.bytes() + Sp.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
+    return (int64_t)(Pf.bytes() + Pb.bytes() + Ubuf.bytes() + d_stasks.bytes() + L.bytes() + Sp.bytes() + CB.bytes() + tinv.bytes() + ywork.bytes() * 3 + uwork.bytes() + d_rows.bytes() * 2 +
                      d_amap.bytes() + d_ea_ptr.bytes() + d_ea_src.bytes() + d_tasks.bytes() + d_sn.bytes());
 }
 

@@ -21,15 +21,24 @@ struct SNDesc {
 // streamed solve (chol_solve.cu): per-supernode descriptor and task (one contiguous byte range of a packed panel)
 struct SolveSN {
     long long pf, pb;   // offsets (doubles) of the packed forward / backward panels (same size, 128-byte aligned)
-    long long u, rows, ell;
+    long long U, pU;    // own contribution buffer [nchild][m] (children write into it); where this supernode writes in its parent's
+    long long rows;
     int m, ns, col0, parent, nchild, child_begin, ntask_f, ntask_b;
 };
+// One TMA copy + everything the consumers need to process it (no further descriptor loads on the critical path).
 struct SolveTask {
     long long src;      // 16-byte aligned offset (doubles) into Pf (kind 0) or Pb (kind 1)
+    long long U, pU;    // contribution buffers: own (read) / slot in the parent's (written)
+    long long rows;     // offset of the supernode's front rows in the row / relative-index arrays
     int s, r0, r1;      // supernode, row range (forward: front rows, backward: columns)
     int ndbl, shift;    // doubles to stream, position of row r0 inside the streamed range
-    int kind;
+    int kind;           // 0 forward, 1 backward
+    int m, ns, col0, nchild;
+    int dep_idx, dep_need;             // wait until counter[dep_idx] >= dep_need (dep_need 0: nothing to wait for)
+    int sig_idx, sig_total, sig_next;  // bump counter[sig_idx]; the bump that makes it sig_total also bumps counter[sig_next] (if >= 0)
+    int g_r1;           // end of the row range covered by the chunk's group
 };
+static_assert(sizeof(SolveTask) == 96, "descriptor copies assume 96 bytes");
 
 struct CholBatch {
     int nmat = 0;
@@ -62,11 +71,11 @@ struct CholBatch {
     // streamed solve
     DevBuf<SolveSN> d_ssn;
     DevBuf<SolveTask> d_stasks;
-    DevBuf<int> d_ell, d_ptasks;
-    DevBuf<double> Pf, Pb;
-    DevBuf<unsigned long long> d_cnt;
+    DevBuf<int> d_ptasks;
+    DevBuf<double> Pf, Pb, Ubuf;
+    DevBuf<unsigned> d_cnt;
     int64_t pk_total = 0;
-    int n_solve_tasks = 0, n_pack_tasks = 0, stage_dbl = 0, solve_grid = 0;
+    int n_solve_tasks = 0, n_pack_tasks = 0, stage_dbl = 0, vec_dbl = 0, solve_grid = 0, solve_nstage = 3, solve_dbg = 0;
     size_t solve_smem = 0;
     void build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st);
     void pack_panels(cudaStream_t st);

@@ -21,6 +21,8 @@
 // All sums have a fixed order (lane-strided partial sums + shuffle tree, children in ascending order): results are
 // bit-reproducible from run to run.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "chol_numeric.h"
 
@@ -28,9 +30,10 @@ namespace dotgpu {
 
 namespace {
 
-constexpr int NSTAGE = 3;
-constexpr int CONSUMERS = 256;
-constexpr int SOLVE_THREADS = CONSUMERS + 32;
+constexpr int SOLVE_GROUP_MAX = 4;  // chunks claimed together (they share one gather of the supernode's vector); queue slots are padded to it
+constexpr int CONSUMERS = 128;   // 4 warps: row . vector products
+constexpr int GATHERERS = 128;   // 4 warps: dependency waits + vector gathers, one supernode ahead of the consumers
+constexpr int SOLVE_THREADS = CONSUMERS + 32 + GATHERERS + 32;  // consumers, producer warp, gatherers, signaller warp
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -64,153 +67,295 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
+__device__ __forceinline__ void gatherer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(GATHERERS) : "memory"); }
 
+// counters: [0,nsn) forward chunks done per supernode, [nsn,2nsn) backward chunks done, [2nsn,3nsn) children whose forward
+// phase is complete, [3nsn] the queue head
+//
+// Warp roles (CTA = 8 consumer warps + producer warp + gatherer warp):
+//   producer  (31 lanes)  claims queue slots, posts chunk descriptors, issues the TMA copies           -> posted[st], full[st]
+//   signaller (1 lane)    publishes finished chunks: fence + completion counters                       <- done[st] -> empty[st]
+//   gatherer  (32 lanes)  per chunk: waits for the chunk's dependency and builds the supernode's vector
+//                         (right-hand side + children updates / ancestors' solution) in shared memory  <- posted[st] -> vready[st]
+//   consumers (256)       row . vector products out of shared memory, results to global memory         <- full, vready -> done[st]
+// The global-memory latencies (queue, descriptors, dependency polls, gathers, fences) all sit in the helper warps and overlap the
+// consumers' work on earlier chunks.
+template <int NSTAGE>
 __global__ void __launch_bounds__(SOLVE_THREADS, 3)
-    k_solve_stream(const SolveTask* __restrict__ tasks, int ntasks, const SolveSN* __restrict__ sn, const int* __restrict__ ell,
-                   const int* __restrict__ child, const int* __restrict__ rows, const double* __restrict__ Pf, const double* __restrict__ Pb,
-                   const double* __restrict__ b, const int* __restrict__ gidx, double* y, double* uwork, double* x,
-                   unsigned long long* cnt, unsigned* claim, int nsn, int stage_dbl) {
+    k_solve_stream(int ngroups, const SolveTask* __restrict__ chunks, const int* __restrict__ rows,
+                   const int* __restrict__ rel, const double* __restrict__ Pf, const double* __restrict__ Pb, const double* __restrict__ b,
+                   const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, unsigned* claim, int stage_dbl,
+                   int vec_dbl, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);          // NSTAGE * stage_dbl
-    double* vec = ring + (size_t)NSTAGE * stage_dbl;              // right-hand side / update vector of the current task
-    __shared__ __align__(8) unsigned long long full[NSTAGE], empty[NSTAGE];
-    __shared__ SolveTask s_task[NSTAGE];
-    __shared__ int s_tid[NSTAGE];
+    double* vecs = ring + (size_t)NSTAGE * stage_dbl;             // 2 x [vec_dbl] vectors (double-buffered across supernodes)
+    int* idxs = reinterpret_cast<int*>(vecs + 2 * (size_t)vec_dbl);  // 2 x [vec_dbl] gather indices / parent positions
+    __shared__ __align__(8) unsigned long long full[NSTAGE], empty[NSTAGE], done[NSTAGE], posted[NSTAGE], vready[NSTAGE];
+    __shared__ SolveTask s_chunk[NSTAGE];
+    __shared__ int s_live[NSTAGE], s_vb[NSTAGE], s_base[NSTAGE];
+    __shared__ __align__(16) SolveTask s_desc[2][SOLVE_GROUP_MAX];
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
+            mbar_init(&done[i], 1);
+            mbar_init(&posted[i], 1);
+            mbar_init(&vready[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid >= CONSUMERS) {
-        // ------------------------------ producer warp: claim + stream ------------------------------
-        if (tid == CONSUMERS) {
-            for (int it = 0;; ++it) {
+    if (tid >= CONSUMERS && tid < CONSUMERS + 31) {
+        // ------------------------------ producer (31 lanes): claim groups, stream their chunks ------------------------------
+        // Everything the producer needs from global memory is requested one group ahead: the queue claim (atomic) and the
+        // group's chunk descriptors (cp.async into a double buffer), so the TMA issue rate is not bound by load latency.
+        constexpr unsigned PM = 0x7fffffffu;
+        const int lane = tid - CONSUMERS;
+        auto fetch = [&](int buf, unsigned g) {
+            if (g < (unsigned)ngroups) {
+                const char* src = reinterpret_cast<const char*>(chunks + (size_t)g * SOLVE_GROUP_MAX);
+                char* dst = reinterpret_cast<char*>(&s_desc[buf][0]);
+                for (int i = lane; i < SOLVE_GROUP_MAX * (int)sizeof(SolveTask) / 16; i += 31)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 16 * i)), "l"(src + 16 * i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        unsigned a = 0;
+        if (lane == 0) a = atomicAdd(claim, 1u);
+        unsigned g0 = __shfl_sync(PM, a, 0);
+        fetch(0, g0);
+        if (lane == 0) a = atomicAdd(claim, 1u);
+        int it = 0, buf = 0;
+        while (g0 < (unsigned)ngroups) {
+            const unsigned g1 = __shfl_sync(PM, a, 0);
+            fetch(buf ^ 1, g1);
+            if (lane == 0) a = atomicAdd(claim, 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp(PM);
+            for (int c = 0; c < SOLVE_GROUP_MAX; ++c) {
+                const SolveTask& T = s_desc[buf][c];
+                const int ndbl = T.ndbl;
+                if (ndbl == 0) continue;  // padding of a short group
+                const int st = it % NSTAGE;
+                if (it >= NSTAGE) {
+                    if (lane == 0) mbar_wait(&empty[st], ((it / NSTAGE) - 1) & 1);
+                    __syncwarp(PM);
+                }
+                if (lane < (int)sizeof(SolveTask) / 4) reinterpret_cast<int*>(&s_chunk[st])[lane] = reinterpret_cast<const int*>(&T)[lane];
+                if (lane == 0) s_live[st] = 1;
+                __syncwarp(PM);
+                if (lane == 0) {
+                    mbar_arrive(&posted[st]);
+                    const unsigned bytes = (unsigned)ndbl * 8u;
+                    if (dbg & 2) {
+                        mbar_arrive(&full[st]);
+                    } else {
+                        mbar_expect_tx(&full[st], bytes);
+                        tma_load_1d(ring + (size_t)st * stage_dbl, (s_chunk[st].kind ? Pb : Pf) + s_chunk[st].src, bytes, &full[st]);
+                    }
+                }
+                ++it;
+            }
+            __syncwarp(PM);
+            g0 = g1;
+            buf ^= 1;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (lane == 0) {
+            // end of stream: a sentinel in every stage (each signaller lane watches one stage)
+            for (int i = 0; i < NSTAGE; ++i, ++it) {
                 const int st = it % NSTAGE;
                 if (it >= NSTAGE) mbar_wait(&empty[st], ((it / NSTAGE) - 1) & 1);
-                const int t = (int)atomicAdd(claim, 1u);
-                s_tid[st] = t;
-                if (t >= ntasks) {
-                    mbar_arrive(&full[st]);
-                    break;
+                s_live[st] = 0;
+                mbar_arrive(&posted[st]);
+                mbar_arrive(&full[st]);
+            }
+        }
+        return;
+    }
+    if (tid == CONSUMERS + 31) return;
+    if (tid >= CONSUMERS + 32 + GATHERERS) {
+        // ------------------------------ signallers: one lane per stage publishes that stage's finished chunks ------------------------------
+        // (release-reduction on the dependency counter of whoever waits for this chunk; off the consumers' critical path, and the
+        //  fences of different stages overlap)
+        const int st = tid - (CONSUMERS + 32 + GATHERERS);
+        if (st >= NSTAGE) return;
+        for (unsigned n = 0;; ++n) {
+            const unsigned par = n & 1;
+            mbar_wait(&posted[st], par);
+            if (!s_live[st]) break;
+            mbar_wait(&done[st], par);  // every consumer has stored its results and left the stage
+            unsigned* p = cnt + s_chunk[st].sig_idx;
+            mbar_arrive(&empty[st]);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+        }
+        return;
+    }
+    if (tid >= CONSUMERS + 32 && tid < CONSUMERS + 32 + GATHERERS) {
+        // ------------------------------ gatherers ------------------------------
+        const int gl = tid - (CONSUMERS + 32);
+        int cur_s = -1, cur_kind = -1, idx_r1 = 0, vb = 1, base = 0, cur_fresh = -1;
+        for (int it = 0;; ++it) {
+            const int st = it % NSTAGE;
+            mbar_wait(&posted[st], (it / NSTAGE) & 1);
+            if (!s_live[st]) break;
+            const SolveTask& T = s_chunk[st];
+            const int m = T.m, ns = T.ns, r0 = T.r0, kind = T.kind, nchild = T.nchild, col0 = T.col0;
+            // a supernode's vector is gathered once and reused by the following chunks of the same phase; the forward phase
+            // also needs the parent positions of the update rows, fetched per group
+            const bool fresh = !(cur_s == T.s && cur_kind == kind) || (kind == 0 && T.r1 > idx_r1);
+            if (fresh) {
+                cur_s = T.s;
+                cur_kind = kind;
+                vb ^= 1;
+                base = r0;
+                // the buffer's previous occupant served the chunks before the previous gather: wait until the consumers left them
+                const int j = cur_fresh - 1;
+                if (j >= 0 && it - j < NSTAGE) mbar_wait(&done[j % NSTAGE], (j / NSTAGE) & 1);
+                cur_fresh = it;
+                double* __restrict__ vec = vecs + (size_t)vb * vec_dbl;
+                int* __restrict__ idx = idxs + (size_t)vb * vec_dbl;
+                const double* __restrict__ Us = U + T.U;
+                // ---- loads that do not depend on other supernodes ----
+                if (kind == 0) {
+                    if (gidx) {
+#pragma unroll 4
+                        for (int k = gl; k < ns; k += GATHERERS) vec[k] = b[gidx[col0 + k]];
+                    } else {
+#pragma unroll 4
+                        for (int k = gl; k < ns; k += GATHERERS) vec[k] = b[col0 + k];
+                    }
+                    idx_r1 = T.g_r1;
+                    const int* __restrict__ prel = rel + T.rows;
+#pragma unroll 4
+                    for (int r = max(r0, ns) + gl; r < idx_r1; r += GATHERERS) idx[r - r0] = prel[r];
+                } else {
+                    const int* __restrict__ frows = rows + T.rows;
+#pragma unroll 4
+                    for (int r = max(r0, ns) + gl; r < m; r += GATHERERS) idx[r - r0] = frows[r];
                 }
-                const SolveTask T = tasks[t];
-                s_task[st] = T;
-                const unsigned bytes = (unsigned)T.ndbl * 8u;
-                mbar_expect_tx(&full[st], bytes);
-                tma_load_1d(ring + (size_t)st * stage_dbl, (T.kind ? Pb : Pf) + T.src, bytes, &full[st]);
+                // ---- dependency: one counter, one expected value ----
+                if (gl == 0 && T.dep_need > 0 && !(dbg & 4)) {
+                    const unsigned need = (unsigned)T.dep_need;
+                    const unsigned* p = cnt + T.dep_idx;
+                    while (ld_acquire(p) < need) {
+                    }
+                }
+                gatherer_sync();
+                // ---- dependent part: contiguous reads of what the children / ancestors published ----
+                if (kind == 0) {
+                    if (nchild > 0) {
+#pragma unroll 2
+                        for (int k = gl; k < ns; k += GATHERERS) {
+                            double v = vec[k];
+                            for (int w = 0; w < nchild; ++w) v += __ldcg(Us + (long long)w * m + k);
+                            vec[k] = v;
+                        }
+                    }
+                    // vec[r], r >= ns: what the children add to update row r (rows of this group only)
+#pragma unroll 2
+                    for (int r = max(r0, ns) + gl; r < idx_r1; r += GATHERERS) {
+                        double v = 0.0;
+                        for (int w = 0; w < nchild; ++w) v += __ldcg(Us + (long long)w * m + r);
+                        vec[r] = v;
+                    }
+                } else {
+#pragma unroll 4
+                    for (int r = r0 + gl; r < m; r += GATHERERS) vec[r - r0] = r < ns ? __ldcg(y + col0 + r) : __ldcg(x + idx[r - r0]);
+                }
+                gatherer_sync();
+            }
+            if (gl == 0) {
+                s_vb[st] = vb;
+                s_base[st] = base;
+                mbar_arrive(&vready[st]);
             }
         }
         return;
     }
 
     // ------------------------------ consumers ------------------------------
-    const int warp = tid >> 5, lane = tid & 31;
-    int verified_s = -1, verified_kind = -1;
+    const int lane = tid & 31;
     for (int it = 0;; ++it) {
         const int st = it % NSTAGE;
-        mbar_wait(&full[st], (it / NSTAGE) & 1);
-        if (s_tid[st] >= ntasks) break;
-        const SolveTask T = s_task[st];
-        const SolveSN d = sn[T.s];
+        const unsigned par = (it / NSTAGE) & 1;
+        mbar_wait(&posted[st], par);
+        if (!s_live[st]) break;
+        mbar_wait(&vready[st], par);
+        mbar_wait(&full[st], par);
+        const SolveTask& T = s_chunk[st];
+        const int m = T.m, ns = T.ns, r0 = T.r0, r1 = T.r1, col0 = T.col0;
+        const int vbase = s_base[st];
+        const double* __restrict__ vec = vecs + (size_t)s_vb[st] * vec_dbl;
+        const int* __restrict__ idx = idxs + (size_t)s_vb[st] * vec_dbl;
         const double* __restrict__ chunk = ring + (size_t)st * stage_dbl + T.shift;
-        // ---- dependencies ----
-        if (!(verified_s == T.s && verified_kind == T.kind)) {
-            if (tid == 0) {
-                if (T.kind == 0) {
-                    for (int ci = 0; ci < d.nchild; ++ci) {
-                        const int c = child[d.child_begin + ci];
-                        const unsigned long long need = (unsigned long long)sn[c].ntask_f;
-                        while (ld_acquire(cnt + c) < need) {
-                        }
-                    }
-                } else if (d.parent >= 0) {
-                    const unsigned long long need = (unsigned long long)sn[d.parent].ntask_b;
-                    while (ld_acquire(cnt + nsn + d.parent) < need) {
-                    }
-                } else {
-                    const unsigned long long need = (unsigned long long)d.ntask_f;
-                    while (ld_acquire(cnt + T.s) < need) {
-                    }
+        // Row . vector products.  W lanes share a row, W = the largest power of two that still gives every row of the chunk its own
+        // lane group (W = 1: one thread per row, no reduction; W = 32: a warp per row).  Short rows dominate the factor (update rows
+        // of leaf-side supernodes), so most chunks run with small W and finish in one pass with a short or no shuffle tree.
+        const int nrows = r1 - r0;
+        int W = 32;
+        while (W > 1 && nrows * W > CONSUMERS) W >>= 1;
+        const int sub = tid / W, sl = tid % W, nsub = CONSUMERS / W;
+        const bool fwd = T.kind == 0;
+        const int tri0 = r0 < ns ? (ns - r0) * (ns + r0 + 1) / 2 : 0;  // forward: entries of the triangle rows r0..ns-1 of this chunk
+        const long long pU = T.pU;
+        if (!(dbg & 1))
+        for (int i0 = 0; i0 < nrows; i0 += nsub) {
+            const int r = r0 + i0 + sub;
+            const bool valid = r < r1;
+            int off = 0, len = 0;
+            const double* __restrict__ v = vec;
+            if (valid) {
+                if (fwd) {  // row r of S: triangle rows hold r+1 entries, update rows ns
+                    off = r < ns ? (r - r0) * (r + r0 + 1) / 2 : tri0 + (r - max(ns, r0)) * ns;
+                    len = r < ns ? r + 1 : ns;
+                } else {    // packed row r of S^T holds rows r..m-1: offset (r - r0)*m - (r(r-1) - r0(r0-1))/2
+                    off = (r - r0) * m - (r * (r - 1) - r0 * (r0 - 1)) / 2;
+                    len = m - r;
+                    v = vec + (r - vbase);
                 }
             }
-            consumer_sync();
-            verified_s = T.s;
-            verified_kind = T.kind;
-        }
-        if (T.kind == 0) {
-            // ================= forward: [y_s ; u_s](rows r0..r1) = S_s(rows) * t,  t = b_s + children updates =================
-            const int tn = min(d.ns, T.r1);
-            const int* __restrict__ esrc = ell + d.ell;
-            for (int k = tid; k < tn; k += CONSUMERS) {
-                double v = gidx ? b[gidx[d.col0 + k]] : b[d.col0 + k];
-                for (int w = 0; w < d.nchild; ++w) {
-                    const int src = esrc[(long long)k * d.nchild + w];
-                    if (src >= 0) v += __ldcg(uwork + src);
+            const double* __restrict__ row = chunk + off;
+            double s0 = 0.0, s1 = 0.0;
+            if (W == 1) {
+                // lane stride in shared memory = row length; for even lengths rotate the start by the lane so that the stride
+                // becomes odd and the accesses stay bank-conflict free
+                int k = (len & 1) == 0 && len > 0 ? lane % len : 0;
+                int i = 0;
+                for (; i + 1 < len; i += 2) {
+                    const int k1 = k + 1 == len ? 0 : k + 1;
+                    s0 += row[k] * v[k];
+                    s1 += row[k1] * v[k1];
+                    k = k1 + 1 == len ? 0 : k1 + 1;
                 }
-                vec[k] = v;
-            }
-            consumer_sync();
-            const long long tri = (long long)d.ns * (d.ns + 1) / 2;
-            const long long base0 = T.r0 < d.ns ? (long long)T.r0 * (T.r0 + 1) / 2 : tri + (long long)(T.r0 - d.ns) * d.ns;
-            for (int r = T.r0 + warp; r < T.r1; r += CONSUMERS / 32) {
-                const long long off = (r < d.ns ? (long long)r * (r + 1) / 2 : tri + (long long)(r - d.ns) * d.ns) - base0;
-                const int kn = r < d.ns ? r + 1 : d.ns;
-                const double* __restrict__ row = chunk + off;
-                double sum = 0.0;
-                for (int k = lane; k < kn; k += 32) sum += row[k] * vec[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-                if (lane == 0) {
-                    if (r < d.ns) {
-                        y[d.col0 + r] = sum;
-                    } else {
-                        double v = 0.0;
-                        for (int w = 0; w < d.nchild; ++w) {
-                            const int src = esrc[(long long)r * d.nchild + w];
-                            if (src >= 0) v += __ldcg(uwork + src);
-                        }
-                        uwork[d.u + (r - d.ns)] = v + sum;
-                    }
+                if (i < len) s0 += row[k] * v[k];
+            } else {
+                int k = sl;
+                for (; k + W < len; k += 2 * W) {
+                    s0 += row[k] * v[k];
+                    s1 += row[k + W] * v[k + W];
                 }
+                if (k < len) s0 += row[k] * v[k];
             }
-        } else {
-            // ================= backward: x_s(cols r0..r1) = S_s^T(cols) * [y_s ; x(rows below)] =================
-            const int c0 = T.r0;
-            const int* __restrict__ frows = rows + d.rows;
-            for (int r = c0 + tid; r < d.m; r += CONSUMERS) vec[r - c0] = r < d.ns ? __ldcg(y + d.col0 + r) : __ldcg(x + frows[r]);
-            consumer_sync();
-            // packed row c of S^T starts at c*m - c(c-1)/2 and holds rows c..m-1
-            const long long base0 = (long long)c0 * d.m - (long long)c0 * (c0 - 1) / 2;
-            for (int c = c0 + warp; c < T.r1; c += CONSUMERS / 32) {
-                const long long off = (long long)c * d.m - (long long)c * (c - 1) / 2 - base0;
-                const double* __restrict__ row = chunk + off;
-                const double* __restrict__ z = vec + (c - c0);
-                const int len = d.m - c;
-                double sum = 0.0;
-                for (int k = lane; k < len; k += 32) sum += row[k] * z[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-                if (lane == 0) x[d.col0 + c] = sum;
+            double sum = s0 + s1;
+            for (int o = W >> 1; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, W);
+            if (valid && sl == 0) {
+                if (!fwd) x[col0 + r] = sum;
+                else if (r < ns) y[col0 + r] = sum;
+                else U[pU + idx[r - vbase]] = vec[r] + sum;
             }
         }
-        consumer_sync();  // all results stored, all shared-memory reads of this stage done
-        if (tid == 0) {
-            mbar_arrive(&empty[st]);
-            __threadfence();
-            atomicAdd(cnt + (T.kind ? nsn : 0) + T.s, 1ull);
-        }
+        consumer_sync();  // all results stored, all shared-memory reads of this stage (data, descriptor, vector) done
+        if (tid == 0) mbar_arrive(&done[st]);
     }
 }
 
@@ -253,23 +398,14 @@ __global__ void __launch_bounds__(256) k_pack_panels(const Task3p* __restrict__ 
 void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st) {
     const int nsn = nsuper_total;
     std::vector<SolveSN> ssn(nsn);
-    std::vector<int> ell;
-    int64_t pf = 0;
+    int64_t pf = 0, ub = 0;
     int max_row = 2;
-    // ELL table of update sources: ell[d.ell + i*nchild + w] = uwork index that child w adds to front row i (or -1)
-    std::vector<int> child_slot(nsn, 0);  // position of a supernode among its parent's children
-    for (int m = 0; m < nmat; ++m) {
-        const Symbolic& S = sym[m];
-        for (int s = 0; s < S.nsuper; ++s)
-            for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) child_slot[sn_off[m] + S.child_list[ci]] = ci - S.child_ptr[s];
-    }
     for (int g = 0; g < nsn; ++g) {
         const SNDesc& d = sn[g];
         SolveSN& o = ssn[g];
         o.m = d.m;
         o.ns = d.ns;
         o.col0 = d.col0;
-        o.u = d.u;
         o.rows = d.rows;
         o.parent = d.parent;
         o.nchild = d.child_end - d.child_begin;
@@ -277,74 +413,144 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
         o.pf = o.pb = pf;
         const int64_t sz = (int64_t)d.ns * (d.ns + 1) / 2 + (int64_t)(d.m - d.ns) * d.ns;
         pf += (sz + 15) & ~15LL;
-        o.ell = (int64_t)ell.size();
-        ell.resize(ell.size() + (size_t)d.m * o.nchild, -1);
+        // contribution buffer: one dense row of length m per child; a child writes only the positions of its own update
+        // rows, everything else stays at the zero it was allocated with
+        o.U = ub;
+        ub += (int64_t)o.nchild * d.m;
+        o.pU = -1;
+        o.ntask_f = o.ntask_b = 0;
         max_row = std::max(max_row, std::max(d.ns, d.m));
     }
-    pk_total = pf;
-    // fill the ELL table from the symbolic relative indices
     for (int m = 0; m < nmat; ++m) {
         const Symbolic& S = sym[m];
-        for (int s = 0; s < S.nsuper; ++s) {
-            const int p = S.parent[s];
-            if (p < 0) continue;
-            const int g = sn_off[m] + s, gp = sn_off[m] + p;
-            const int ns = S.nscol(s);
-            for (int64_t o = S.row_ptr[s] + ns; o < S.row_ptr[s + 1]; ++o) {
-                const int64_t src = sn[g].u + (o - S.row_ptr[s] - ns);
-                DG_REQUIRE(src < (1LL << 31), "update workspace too large for 32-bit indices");
-                ell[ssn[gp].ell + (int64_t)S.rel[o] * ssn[gp].nchild + child_slot[g]] = (int)src;
+        for (int s = 0; s < S.nsuper; ++s)
+            for (int ci = S.child_ptr[s]; ci < S.child_ptr[s + 1]; ++ci) {
+                const int gp = sn_off[m] + s, gc = sn_off[m] + S.child_list[ci];
+                ssn[gc].pU = ssn[gp].U + (int64_t)(ci - S.child_ptr[s]) * ssn[gp].m;
             }
-        }
     }
-    // ---- tasks: forward levels ascending, backward levels descending ----
-    stage_dbl = std::max(2048, ((max_row + 2 + 15) / 16) * 16);
-    DG_REQUIRE((size_t)NSTAGE * stage_dbl * 8 + (size_t)(max_front_all + 8) * 8 <= 200 * 1024, "front too large for the streamed solve");
-    std::vector<SolveTask> tasks;
+    pk_total = pf;
+    // ---- chunks (one TMA copy each) and groups (claimed as a unit; the vector of a supernode is gathered once per group) ----
+    // tuning knobs (defaults measured on B200): stage size in doubles, ring depth, chunks per claimed group
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = std::getenv(name);
+        return v && *v ? std::atoi(v) : dflt;
+    };
+    const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", 2560);
+    solve_dbg = env_int("DOTGPU_SOLVE_DBG", 0);  // experiments only: 1 skip the products, 2 skip the TMA copies, 4 skip dependency waits
+    solve_nstage = std::min(4, std::max(2, env_int("DOTGPU_SOLVE_NSTAGE", 2)));
+    const int max_group = std::min(SOLVE_GROUP_MAX, std::max(1, env_int("DOTGPU_SOLVE_GROUP", SOLVE_GROUP_MAX)));
+    stage_dbl = std::max((want_stage + 15) / 16 * 16, ((max_row + 2 + 15) / 16) * 16);
+    vec_dbl = ((max_front_all + 8 + 15) / 16) * 16;
+    solve_smem = (size_t)solve_nstage * stage_dbl * 8 + 2 * (size_t)vec_dbl * 12;
+    DG_REQUIRE(solve_smem <= 200 * 1024, "front too large for the streamed solve");
+    std::vector<SolveTask> chunks;
     auto fwd_off = [](const SolveSN& d, int r) -> int64_t {
         return r < d.ns ? (int64_t)r * (r + 1) / 2 : (int64_t)d.ns * (d.ns + 1) / 2 + (int64_t)(r - d.ns) * d.ns;
     };
     auto bwd_off = [](const SolveSN& d, int c) -> int64_t { return (int64_t)c * d.m - (int64_t)c * (c - 1) / 2; };
+    const int max_rows_chunk = vec_dbl;  // idxbuf holds one entry per row of a chunk
+    int group_chunks = 1;
+    size_t group_start = 0;
+    SolveTask null_chunk;
+    std::memset(&null_chunk, 0, sizeof(null_chunk));
     auto emit = [&](int g, int kind) {
         SolveSN& d = ssn[g];
         const int nrows = kind ? d.ns : d.m;
-        int cntt = 0;
-        int r0 = 0;
+        auto off_of = [&](int r) { return kind ? bwd_off(d, r) : fwd_off(d, r); };  // offset of row r = one past row r-1
+        int cntt = 0, r0 = 0;
         while (r0 < nrows) {
-            const int64_t o0 = kind ? bwd_off(d, r0) : fwd_off(d, r0);
+            const int64_t o0 = off_of(r0);
             const int64_t a0 = o0 & ~1LL;  // 16-byte aligned start (panel bases are 128-byte aligned)
             int r1 = r0 + 1;
-            auto end_of = [&](int r) { return kind ? bwd_off(d, r) : fwd_off(d, r); };  // offset one past row r-1
-            while (r1 < nrows && ((end_of(r1 + 1) + 1) & ~1LL) - a0 <= stage_dbl) ++r1;
-            const int64_t e1 = (end_of(r1) + 1) & ~1LL;
+            while (r1 < nrows && r1 - r0 < max_rows_chunk && ((off_of(r1 + 1) + 1) & ~1LL) - a0 <= stage_dbl) ++r1;
+            const int64_t e1 = (off_of(r1) + 1) & ~1LL;
             SolveTask T;
             T.src = (kind ? d.pb : d.pf) + a0;
+            T.U = d.U;
+            T.pU = d.pU;
+            T.rows = d.rows;
             T.s = g;
             T.r0 = r0;
             T.r1 = r1;
             T.ndbl = (int)(e1 - a0);
             T.shift = (int)(o0 - a0);
             T.kind = kind;
-            DG_REQUIRE(T.ndbl <= stage_dbl, "solve task exceeds the stage size");
-            tasks.push_back(T);
+            T.m = d.m;
+            T.ns = d.ns;
+            T.col0 = d.col0;
+            T.nchild = d.nchild;
+            T.dep_idx = T.dep_need = T.sig_idx = T.sig_total = 0;  // filled once the chunk counts are known
+            T.sig_next = -1;
+            T.g_r1 = 0;
+            DG_REQUIRE(T.ndbl <= stage_dbl, "solve chunk exceeds the stage size");
+            if (cntt % group_chunks == 0) {  // open a new queue slot: pad the previous one to SOLVE_GROUP_MAX descriptors
+                while (chunks.size() % SOLVE_GROUP_MAX) chunks.push_back(null_chunk);
+                group_start = chunks.size();
+            }
+            chunks.push_back(T);
+            for (size_t c = group_start; c < chunks.size(); ++c) chunks[c].g_r1 = r1;  // last row of the group so far
             ++cntt;
             r0 = r1;
         }
         (kind ? d.ntask_b : d.ntask_f) = cntt;
     };
-    for (int lv = 0; lv < nlevels; ++lv)
+    int dev = 0, nsm = 0;
+    DG_CUDA(cudaGetDevice(&dev));
+    DG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    // groups of up to SOLVE_GROUP_CHUNKS chunks where a level has far more chunks than CTAs, single chunks near the root
+    auto level_pass = [&](int lv, int kind) {
+        int64_t dbl = 0;
         for (int m = 0; m < nmat; ++m) {
             const Symbolic& S = sym[m];
             if (lv >= S.nlevels) continue;
-            for (int i = S.level_ptr[lv]; i < S.level_ptr[lv + 1]; ++i) emit(sn_off[m] + S.level_list[i], 0);
+            for (int i = S.level_ptr[lv]; i < S.level_ptr[lv + 1]; ++i) {
+                const SolveSN& d = ssn[sn_off[m] + S.level_list[i]];
+                dbl += (int64_t)d.ns * (d.ns + 1) / 2 + (int64_t)(d.m - d.ns) * d.ns;
+            }
         }
-    for (int lv = nlevels - 1; lv >= 0; --lv)
+        const int64_t nch = dbl / stage_dbl + 1;
+        group_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_group, nch / (6LL * nsm)));
         for (int m = 0; m < nmat; ++m) {
             const Symbolic& S = sym[m];
             if (lv >= S.nlevels) continue;
-            for (int i = S.level_ptr[lv]; i < S.level_ptr[lv + 1]; ++i) emit(sn_off[m] + S.level_list[i], 1);
+            for (int i = S.level_ptr[lv]; i < S.level_ptr[lv + 1]; ++i) emit(sn_off[m] + S.level_list[i], kind);
         }
-    n_solve_tasks = (int)tasks.size();
+    };
+    for (int lv = 0; lv < nlevels; ++lv) level_pass(lv, 0);
+    for (int lv = nlevels - 1; lv >= 0; --lv) level_pass(lv, 1);
+    while (chunks.size() % SOLVE_GROUP_MAX) chunks.push_back(null_chunk);
+    n_solve_tasks = (int)(chunks.size() / SOLVE_GROUP_MAX);
+    // dependency counters: every finished chunk bumps exactly one counter (fire-and-forget release reduction):
+    //   forward chunk of s   -> the parent's "children chunks done" counter [2nsn + parent]   (a root: its own [s])
+    //   backward chunk of s  -> its own [nsn + s]
+    // and every chunk waits for one counter to reach one value:
+    //   forward of s  : [2nsn + s] == sum of the children's forward chunk counts
+    //   backward of s : [nsn + parent] == the parent's backward chunk count (which transitively waited for every forward phase
+    //                   of the tree);  a root waits for its own forward phase [s] == ntask_f
+    std::vector<int> child_chunks(nsn, 0);
+    for (int g = 0; g < nsn; ++g)
+        if (ssn[g].parent >= 0) child_chunks[ssn[g].parent] += ssn[g].ntask_f;
+    for (SolveTask& T : chunks) {
+        if (T.ndbl == 0) continue;
+        const SolveSN& d = ssn[T.s];
+        if (T.kind == 0) {
+            T.dep_idx = 2 * nsn + T.s;
+            T.dep_need = child_chunks[T.s];
+            T.sig_idx = d.parent >= 0 ? 2 * nsn + d.parent : T.s;
+        } else {
+            if (d.parent >= 0) {
+                T.dep_idx = nsn + d.parent;
+                T.dep_need = ssn[d.parent].ntask_b;
+            } else {
+                T.dep_idx = T.s;
+                T.dep_need = d.ntask_f;
+            }
+            T.sig_idx = nsn + T.s;
+        }
+        T.sig_total = 0;
+        T.sig_next = -1;
+    }
     // pack tasks
     std::vector<int> ptasks;
     for (int g = 0; g < nsn; ++g)
@@ -356,23 +562,24 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
                 }
     n_pack_tasks = (int)ptasks.size() / 2;
     if (ptasks.empty()) ptasks.push_back(0);
-    if (tasks.empty()) tasks.push_back(SolveTask());
-    if (ell.empty()) ell.push_back(-1);
+    if (chunks.empty()) chunks.assign(SOLVE_GROUP_MAX, null_chunk);
     d_ssn.upload(ssn, st);
-    d_ell.upload(ell, st);
-    d_stasks.upload(tasks, st);
+    d_stasks.upload(chunks, st);
     d_ptasks.upload(ptasks, st);
     Pf.alloc(std::max<int64_t>(pk_total, 16));
     Pb.alloc(std::max<int64_t>(pk_total, 16));
     DG_CUDA(cudaMemsetAsync(Pf.p, 0, Pf.bytes(), st));  // alignment padding is streamed too: keep it finite
     DG_CUDA(cudaMemsetAsync(Pb.p, 0, Pb.bytes(), st));
-    d_cnt.alloc(2 * (size_t)std::max(nsn, 1) + 2);
-    solve_smem = (size_t)NSTAGE * stage_dbl * 8 + (size_t)(max_front_all + 8) * 8;
-    DG_CUDA(cudaFuncSetAttribute(k_solve_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    int dev = 0, nsm = 0, per_sm = 0;
-    DG_CUDA(cudaGetDevice(&dev));
-    DG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_stream, SOLVE_THREADS, solve_smem));
+    Ubuf.alloc(std::max<int64_t>(ub, 1));
+    Ubuf.zero(st);
+    d_cnt.alloc(3 * (size_t)std::max(nsn, 1) + 2);
+    DG_CUDA(cudaFuncSetAttribute(k_solve_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DG_CUDA(cudaFuncSetAttribute(k_solve_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DG_CUDA(cudaFuncSetAttribute(k_solve_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 0;
+    if (solve_nstage == 2) DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_stream<2>, SOLVE_THREADS, solve_smem));
+    else if (solve_nstage == 3) DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_stream<3>, SOLVE_THREADS, solve_smem));
+    else DG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_stream<4>, SOLVE_THREADS, solve_smem));
     DG_REQUIRE(per_sm >= 1, "streamed solve kernel does not fit on an SM");
     solve_grid = std::min(nsm * per_sm, std::max(1, n_solve_tasks));
 }
@@ -387,9 +594,14 @@ void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStre
     if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
     if (!n_solve_tasks) return;
     DG_CUDA(cudaMemsetAsync(d_cnt.p, 0, d_cnt.bytes(), st));
-    unsigned* claim = reinterpret_cast<unsigned*>(d_cnt.p + 2 * (size_t)std::max(nsuper_total, 1));
-    k_solve_stream<<<solve_grid, SOLVE_THREADS, solve_smem, st>>>(d_stasks.p, n_solve_tasks, d_ssn.p, d_ell.p, d_child.p, d_rows.p, Pf.p, Pb.p, b, gidx,
-                                                                   ywork.p, uwork.p, x_perm, d_cnt.p, claim, nsuper_total, stage_dbl);
+    unsigned* claim = d_cnt.p + 3 * (size_t)std::max(nsuper_total, 1);
+#define DG_SOLVE_LAUNCH(NS)                                                                                                         \
+    k_solve_stream<NS><<<solve_grid, SOLVE_THREADS, solve_smem, st>>>(n_solve_tasks, d_stasks.p, d_rows.p, d_rel.p, Pf.p, Pb.p, b, \
+                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg)
+    if (solve_nstage == 2) DG_SOLVE_LAUNCH(2);
+    else if (solve_nstage == 3) DG_SOLVE_LAUNCH(3);
+    else DG_SOLVE_LAUNCH(4);
+#undef DG_SOLVE_LAUNCH
     count_launch();
 }
 

@@ -23,6 +23,7 @@ struct DeviceMesh {
     DevBuf<double> He;      // 144*nT, allocated on first use
     DevBuf<double> partial; // block partial sums for reductions
     int n_partial = 0;
+    DevBuf<unsigned> counter;  // last-block detection of the fused energy reduction (self-resetting)
 
     void init(int energy_type, int nV_, int nT_, const int32_t* tets_h, const double* DmInv_rowmajor, const double* vol_h,
               const double* mu_h, const double* lam_h, const double* mass_h, const unsigned char* fixed_h, cudaStream_t st);

@@ -61,50 +61,58 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return r;
 }
 
+// K1: incremental potential in ONE launch.  Blocks [0, nbT) evaluate vol_t*Psi_t of TPB tets each, blocks [nbT, nbT+nbV)
+// the inertia term of 256... (TPB) vertices each (sum_v m_v |x_v - xTilde_v|^2 / 2 over ALL vertices, Optimizer.cpp:1204-1211);
+// every block stores its partial sum, the last block to finish adds them in a fixed order:
+//   out = coef * sum(partial[0..nbT)) + sum(partial[nbT..nbT+nbV))          (deterministic, bit-reproducible)
 template <int EN>
-__global__ void __launch_bounds__(TPB) k_energy(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+__global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
                                                 const double* __restrict__ vol, const double* __restrict__ mu,
                                                 const double* __restrict__ lam, const double* __restrict__ x,
-                                                double* __restrict__ partial, double* __restrict__ per_elem) {
+                                                const double* __restrict__ xt, const double* __restrict__ mass, double coef,
+                                                double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ out,
+                                                double* __restrict__ per_elem) {
     __shared__ double sh[TPB / 32];
-    int t = blockIdx.x * TPB + threadIdx.x;
+    __shared__ bool last;
     double e = 0.0;
-    if (t < nT) {
-        TetIn in;
-        load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
-        e = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
-        if (per_elem) per_elem[t] = e;
+    if ((int)blockIdx.x < nbT) {
+        int t = blockIdx.x * TPB + threadIdx.x;
+        if (t < nT) {
+            TetIn in;
+            load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+            e = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
+            if (per_elem) per_elem[t] = e;
+        }
+    } else {
+        int v = (blockIdx.x - nbT) * TPB + threadIdx.x;
+        if (v < nV) {
+            double a = x[3 * (size_t)v] - xt[3 * (size_t)v], b = x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1],
+                   c = x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2];
+            e = (a * a + b * b + c * c) * mass[v] / 2.0;
+        }
     }
     double s = block_sum<TPB>(e, sh);
-    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = s;
-}
-
-// inertia energy sum_v m_v |x_v - xTilde_v|^2 / 2 over ALL vertices (Optimizer.cpp:1204-1211)
-__global__ void __launch_bounds__(256) k_inertia_energy(int nV, const double* __restrict__ x, const double* __restrict__ xt,
-                                                        const double* __restrict__ mass, double* __restrict__ partial) {
-    __shared__ double sh[8];
-    int v = blockIdx.x * 256 + threadIdx.x;
-    double e = 0.0;
-    if (v < nV) {
-        double a = x[3 * (size_t)v] - xt[3 * (size_t)v], b = x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1],
-               c = x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2];
-        e = (a * a + b * b + c * c) * mass[v] / 2.0;
+    if (!out) return;  // per-element mode
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     }
-    double s = block_sum<256>(e, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-
-// out = coef * sum(partial[0..n1)) + sum(partial[n1..n1+n2))   single CTA, fixed order
-__global__ void __launch_bounds__(256) k_final_sum(const double* __restrict__ partial, int n1, int n2, double coef,
-                                                   double* __restrict__ out) {
-    __shared__ double sh[8];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < n1; i += 256) a += partial[i];
-    for (int i = threadIdx.x; i < n2; i += 256) b += partial[n1 + i];
-    double sa = block_sum<256>(a, sh);
     __syncthreads();
-    double sb = block_sum<256>(b, sh);
-    if (threadIdx.x == 0) out[0] = coef * sa + sb;
+    if (!last) return;
+    __threadfence();
+    const int nb = gridDim.x;
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nbT; i += TPB) a += __ldcg(partial + i);
+    for (int i = nbT + threadIdx.x; i < nb; i += TPB) b += __ldcg(partial + i);
+    __syncthreads();
+    double sa = block_sum<TPB>(a, sh);
+    __syncthreads();
+    double sb = block_sum<TPB>(b, sh);
+    if (threadIdx.x == 0) {
+        out[0] = coef * sa + sb;
+        *counter = 0u;
+    }
 }
 
 template <int EN>
@@ -274,8 +282,10 @@ void DeviceMesh::init(int energy_type, int nV_, int nT_, const int32_t* tets_h, 
     vf_ptr.upload(ptr, st);
     vf_idx.upload(idx, st);
     ge.alloc((size_t)12 * nT);
-    n_partial = ceil_div(nT, TPB) + ceil_div(nV, 256);
+    n_partial = ceil_div(nT, TPB) + ceil_div(nV, TPB);
     partial.alloc(n_partial);
+    counter.alloc(1);
+    counter.zero(st);
     DG_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -294,23 +304,15 @@ void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
     } while (0)
 
 void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st) {
-    int nb = ceil_div(m.nT, TPB);
-    DISPATCH_EN(m, k_energy, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, m.partial.p,
-                (double*)nullptr);
-    int nb2 = 0;
-    if (xTilde) {
-        nb2 = ceil_div(m.nV, 256);
-        k_inertia_energy<<<nb2, 256, 0, st>>>(m.nV, x, xTilde, m.mass.p, m.partial.p + nb);
-        count_launch();
-    }
-    k_final_sum<<<1, 256, 0, st>>>(m.partial.p, nb, nb2, coef, E_out);
-    count_launch();
+    const int nbT = ceil_div(m.nT, TPB), nbV = xTilde ? ceil_div(m.nV, TPB) : 0;
+    DISPATCH_EN(m, k_energy, nbT + nbV, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, xTilde,
+                m.mass.p, coef, m.partial.p, m.counter.p, E_out, (double*)nullptr);
 }
 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st) {
-    int nb = ceil_div(m.nT, TPB);
-    DISPATCH_EN(m, k_energy, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
-                (double*)nullptr, out);
+    const int nbT = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_energy, nbT, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
+                (const double*)nullptr, (const double*)nullptr, 1.0, (double*)nullptr, (unsigned*)nullptr, (double*)nullptr, out);
 }
 
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st) {

@@ -109,7 +109,7 @@ int dotgpu_solver_multiply(dotgpu_solver* s, const double* x, double* y);
 /* introspection (what SURVEY.md App. A.10 reads from cholmod_factor): */
 typedef struct dotgpu_solver_info {
     int32_t n, nsuper, nlevels, max_front, max_nscol;
-    int64_t nnz_a, nnz_l;     /* entries stored in the supernodal panels */
+    int64_t nnz_a, nnz_l;     /* nnz of A's stored triangle; nnz of the supernodal factor L (packed triangles + sub-diagonal blocks) */
     double flops;             /* factorisation flops */
     int64_t device_bytes;
 } dotgpu_solver_info;

@@ -16,6 +16,7 @@
 
 #include <Eigen/Eigen>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -46,8 +47,36 @@ protected:
         h = nullptr;
         values_fresh = false;
     }
+    // CHOLMOD is handed the base class's arrays as a CSC matrix with stype=-1, i.e. it reads ONLY entries with row >= column
+    // (CHOLMODSolver.cpp:95-105) - callers of set_pattern(SparseMatrix) may store more (ADMM's consensus matrix).  The C ABI wants
+    // exactly that triangle as CSR-upper with ascending columns and the diagonal first, so filter once per pattern.
+    std::vector<int32_t> cia, cja;
+    std::vector<int> keep;  // position in Base::a of every kept entry
+    std::vector<double> vals;
     void ensure() {
-        if (!h) check(dotgpu_solver_create(&h, dropin_device(), Base::numRows, Base::ia.data(), Base::ja.data()), "solver_create");
+        if (h) return;
+        const int n = Base::numRows;
+        cia.assign(n + 1, 0);
+        cja.clear();
+        keep.clear();
+        std::vector<std::pair<int, int>> row;
+        for (int i = 0; i < n; ++i) {
+            row.clear();
+            for (int k = Base::ia[i]; k < Base::ia[i + 1]; ++k)
+                if (Base::ja[k] >= i) row.emplace_back(Base::ja[k], k);
+            std::sort(row.begin(), row.end());
+            for (const auto& e : row) {
+                cja.push_back(e.first);
+                keep.push_back(e.second);
+            }
+            cia[i + 1] = (int32_t)cja.size();
+        }
+        vals.resize(keep.size());
+        check(dotgpu_solver_create(&h, dropin_device(), n, cia.data(), cja.data()), "solver_create");
+    }
+    void push_values() {
+        for (size_t k = 0; k < keep.size(); ++k) vals[k] = Base::a[keep[k]];
+        check(dotgpu_solver_set_values(h, vals.data()), "solver_set_values");
     }
 
 public:
@@ -81,7 +110,7 @@ public:
     }
     bool factorize(void) {  // cholmod_factorize on the current values of `a`
         ensure();
-        check(dotgpu_solver_set_values(h, Base::a.data()), "solver_set_values");
+        push_values();
         const int rc = dotgpu_solver_factorize(h);
         if (rc != DOTGPU_OK && rc != DOTGPU_ERR_NOT_SPD) check(rc, "solver_factorize");
         values_fresh = true;
@@ -98,7 +127,7 @@ public:
     virtual void multiply(const Eigen::VectorXd& x, Eigen::VectorXd& Ax) {  // cholmod_sdmult with stype=-1: symmetric SpMV
         ensure();
         // callers modify `a` through get_a()/addCoeff between calls (it is never factorised under DOT)
-        check(dotgpu_solver_set_values(h, Base::a.data()), "solver_set_values");
+        push_values();
         Ax.conservativeResize(Base::numRows);
         check(dotgpu_solver_multiply(h, x.data(), Ax.data()), "solver_multiply");
     }

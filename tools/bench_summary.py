@@ -1,0 +1,10 @@
+import json, sys
+for fn in sys.argv[1:]:
+    try:
+        d = json.load(open(fn))
+    except Exception as e:
+        print(fn, "ERR", e); continue
+    print(fn.split("/")[-1], "fps %.2f e2e %.2f ms/step %.2f iters %d conv %s launches %d solve_ms %.2f refresh_ms %.2f" % (
+        d["value"], d["e2e"]["value"], d["ms_per_step"], d["inner_iters"], d["all_frames_converged"], d["gpu_launches"], d["solve_ms_per_step"], d["refresh_ms_per_step"]))
+    for k, v in d["kernels"].items():
+        print("     %-14s" % k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a != "algorithmic_bytes"})
