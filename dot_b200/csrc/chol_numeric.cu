@@ -13,6 +13,9 @@
 // forward [y_s; u_s] = S_s (b_s + children updates) with the children gathered deterministically by the parent,
 // backward x_s = S_s^T [y_s; x(rows below)].
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 
 #include "chol_numeric.h"
 
@@ -94,11 +97,29 @@ __global__ void __launch_bounds__(256) k_extend_add(const Task2* __restrict__ ta
         const double* __restrict__ ccb = CB + c.cb;
         for (int i = i0 + warp; i < i1; i += 8) {
             const int r = crel[i];
-            for (int j = lane; j <= i; j += 32) {
-                const int cc = crel[j];
-                double v = ccb[(long long)i * nbc + j];
-                if (cc < p.ns) L[p.panel + (long long)r * p.ns + cc] += v;
-                else CB[p.cb + (long long)(r - p.ns) * nbp + (cc - p.ns)] += v;
+            double* __restrict__ prow_l = L + p.panel + (long long)r * p.ns;
+            double* __restrict__ prow_c = CB + p.cb + (long long)(r - p.ns) * nbp - p.ns;
+            const double* __restrict__ crow = ccb + (long long)i * nbc;
+            // four independent read-modify-writes in flight per lane (targets of one child row are distinct)
+            for (int jb = lane; jb <= i; jb += 128) {
+                double* ptr[4];
+                double v[4], o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = jb + 32 * q;
+                    ptr[q] = nullptr;
+                    v[q] = 0.0;
+                    if (j <= i) {
+                        const int cc = crel[j];
+                        ptr[q] = cc < p.ns ? prow_l + cc : prow_c + cc;
+                        v[q] = crow[j];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = ptr[q] ? *ptr[q] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (ptr[q]) *ptr[q] = o[q] + v[q];
             }
         }
         __syncthreads();
@@ -120,8 +141,11 @@ __device__ __forceinline__ void smem_gemm(double* C, const double* A, int lda, c
 
 constexpr int POTRF_SMEM = (2 * 64 * 65 + 32 * 33) * (int)sizeof(double);
 
+// potrf of pivot tile kb (+ its inverse), one CTA per supernode.  Left-looking column sweep with ONE CTA barrier per
+// column: 4 threads share a row, every row group also recomputes the pivot (row j . row j) itself, so nobody waits for a
+// "pivot thread"; column j is final as soon as its own dot products are subtracted and scaled.
 __global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, int kb, const SNDesc* __restrict__ sn,
-                                               double* __restrict__ L, double* __restrict__ tinv, int* __restrict__ status) {
+                                               double* __restrict__ L, double* __restrict__ tinv, int* __restrict__ status, int dbg) {
     extern __shared__ double smem[];
     double* T = smem;                  // [64][65] tile, then its Cholesky factor
     double* X = smem + 64 * 65;        // [64][65] inverse of the factor
@@ -131,34 +155,95 @@ __global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, in
     const int c0 = kb * NB;
     const int w = min(NB, d.ns - c0);
     double* __restrict__ tile = L + d.panel + (long long)c0 * d.ns + c0;
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-        int r = e >> 6, c = e & 63;
-        double v = 0.0;
-        if (r < w && c <= r) v = tile[(long long)r * d.ns + c];
-        else if (r >= w && c == r) v = 1.0;  // identity padding keeps the blocked inverse well defined
-        T[r * 65 + c] = v;
-        X[r * 65 + c] = 0.0;
+    {
+        double v[16];  // all 16 loads of a thread in flight together
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = threadIdx.x + 256 * i, r = e >> 6, c = e & 63;
+            v[i] = (r < w && c <= r) ? tile[(long long)r * d.ns + c] : ((r >= w && c == r) ? 1.0 : 0.0);  // identity padding
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = threadIdx.x + 256 * i, r = e >> 6, c = e & 63;
+            T[r * 65 + c] = v[i];
+            X[r * 65 + c] = 0.0;
+        }
     }
     __syncthreads();
-    const int ti = threadIdx.x >> 4, tk = threadIdx.x & 15;
-    for (int j = 0; j < w; ++j) {
-        if (threadIdx.x == 0) {
-            double a = T[j * 65 + j];
-            if (!(a > 0.0)) { atomicCAS(status, 0, s + 1); a = 1.0; }
-            T[j * 65 + j] = sqrt(a);
+    if (!(dbg & 1)) {
+        // Left-looking sweep in block columns of 8 (3 CTA barriers per block column, 24 in all, instead of one per column):
+        //   A  every row (4 lanes per row) subtracts its dot products with the 8 pivot rows over the finished columns k < J0
+        //   B  every thread factors the updated 8x8 diagonal block redundantly in registers (no communication)
+        //   C  and solves its own row against it: x = u L_D^-T (for a row of the diagonal block this reproduces L_D's row)
+        const int row = threadIdx.x >> 2, q = threadIdx.x & 3;
+        double* __restrict__ Ti = T + row * 65;
+        for (int J0 = 0; J0 < w; J0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+            for (int k = q; k < J0; k += 4) {
+                const double a = Ti[k];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] += a * T[(J0 + c) * 65 + k];
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+                acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+            }
+            if (q == 0 && row >= J0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (J0 + c <= row) Ti[J0 + c] -= acc[c];
+            }
+            __syncthreads();
+            double D[8][8], u[8], x[8], inv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = Ti[J0 + c];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) D[r][c] = T[(J0 + r) * 65 + J0 + c];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double dd = D[c][c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) dd -= D[c][k] * D[c][k];
+                if (!(dd > 0.0)) {
+                    bad = bad || (J0 + c < w);
+                    dd = 1.0;
+                }
+                const double rs = rsqrt(dd);
+                inv[c] = rs;
+                D[c][c] = dd * rs;
+#pragma unroll
+                for (int r = c + 1; r < 8; ++r) {
+                    double v = D[r][c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) v -= D[r][k] * D[c][k];
+                    D[r][c] = v * rs;
+                }
+            }
+            if (bad && threadIdx.x == 0) atomicCAS(status, 0, s + 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double v = u[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) v -= x[k] * D[c][k];
+                x[c] = v * inv[c];
+            }
+            __syncthreads();  // everybody holds the diagonal block in registers before its rows are overwritten
+            if (q == 0 && row >= J0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (J0 + c <= row) Ti[J0 + c] = x[c];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const double inv = 1.0 / T[j * 65 + j];
-        for (int i = j + 1 + threadIdx.x; i < w; i += 256) T[i * 65 + j] *= inv;
-        __syncthreads();
-        for (int i = j + 1 + ti; i < w; i += 16) {
-            const double lij = T[i * 65 + j];
-            for (int k = j + 1 + tk; k <= i; k += 16) T[i * 65 + k] -= lij * T[k * 65 + j];
-        }
-        __syncthreads();
     }
     // blocked inverse: four 16x16 diagonal blocks by forward substitution (one thread per column) ...
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < 64 && !(dbg & 2)) {
         const int c = threadIdx.x, b0 = c & ~15;
         X[c * 65 + c] = 1.0 / T[c * 65 + c];
         for (int i = c + 1; i < b0 + 16; ++i) {
@@ -169,6 +254,7 @@ __global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, in
     }
     __syncthreads();
     // ... then inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1] at 32 and at 64
+    if (!(dbg & 4)) {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int o = 32 * p;
@@ -181,6 +267,7 @@ __global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, in
     __syncthreads();
     smem_gemm<32, 65>(X + 32 * 65, X + 32 * 65 + 32, 65, W, 33, -1.0);
     __syncthreads();
+    }
     double* __restrict__ tinvp = tinv + d.tinv + (long long)kb * NB * NB;
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {
         int r = e >> 6, c = e & 63;
@@ -255,6 +342,46 @@ __global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks,
         mma_chunk(acc, sA, sB, wr, wc, lane);
     }
     const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int rr = wr * 32 + i * 8 + g, cc = wc * 32 + j * 8 + 2 * q + e;
+                if (rr < nrows && cc < ncols) {
+                    int r = r0 + rr, c = q0 + cc;
+                    if (r >= c && c < d.ns) L[d.panel + (long long)r * d.ns + c] -= acc[i][j][e];  // CB: see k_update_cb
+                }
+            }
+}
+
+// ---- contribution block: CB = -L_below L_below^T in ONE pass over all pivot columns of the supernode (K = ns), after the
+// panel is final.  Every CB tile is accumulated in registers and written once (the per-pivot-step updates above only touch
+// the panel columns), which gives the DMMA tiles a long K loop instead of 64-wide read-modify-write passes. ----
+__global__ void __launch_bounds__(128) k_update_cb(const Task3* __restrict__ tasks, const SNDesc* __restrict__ sn,
+                                                   const double* __restrict__ L, double* __restrict__ CB) {
+    __shared__ double sA[64 * SLD], sB[64 * SLD];
+    const Task3 tk = tasks[blockIdx.x];
+    const SNDesc d = sn[tk.s];
+    const int r0 = d.ns + tk.a * 64, q0 = d.ns + tk.b * 64;
+    const int nrows = min(64, d.m - r0), ncols = min(64, d.m - q0);
+    const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns;
+    const double* __restrict__ B = L + d.panel + (long long)q0 * d.ns;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < d.ns; k0 += KC) {
+        __syncthreads();
+        load_chunk(sA, A + k0, d.ns, nrows, d.ns - k0);
+        load_chunk(sB, B + k0, d.ns, ncols, d.ns - k0);
+        __syncthreads();
+        mma_chunk(acc, sA, sB, wr, wc, lane);
+    }
+    const int g = lane >> 2, q = lane & 3;
     const int nb = d.m - d.ns;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -265,11 +392,7 @@ __global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks,
                 int rr = wr * 32 + i * 8 + g, cc = wc * 32 + j * 8 + 2 * q + e;
                 if (rr < nrows && cc < ncols) {
                     int r = r0 + rr, c = q0 + cc;
-                    if (r >= c) {
-                        double* p = (c < d.ns) ? (L + d.panel + (long long)r * d.ns + c)
-                                               : (CB + d.cb + (long long)(r - d.ns) * nb + (c - d.ns));
-                        *p -= acc[i][j][e];
-                    }
+                    if (r >= c) CB[d.cb + (long long)(r - d.ns) * nb + (c - d.ns)] -= acc[i][j][e];
                 }
             }
 }
@@ -596,13 +719,23 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
             P.update[kb].off = (int)tasks.size();
             for (int s : sns)
                 if (kb * NB < sn[s].ns) {
+                    const int base = std::min((kb + 1) * NB, sn[s].ns);
                     int nt = 0;
-                    while (std::min((kb + 1) * NB, sn[s].ns) + nt * 64 < sn[s].m) ++nt;
+                    while (base + nt * 64 < sn[s].m) ++nt;
                     for (int a = 0; a < nt; ++a)
-                        for (int b = 0; b <= a; ++b) push2(s, (a & 0xffff) | (b << 16));
+                        for (int b = 0; b <= a; ++b)
+                            if (base + b * 64 < sn[s].ns) push2(s, (a & 0xffff) | (b << 16));  // panel columns only
                 }
             P.update[kb].cnt = ((int)tasks.size() - P.update[kb].off) / 2;
         }
+        P.update_cb.off = (int)tasks.size();
+        for (int s : sns) {
+            int nt = 0;
+            while (sn[s].ns + nt * 64 < sn[s].m) ++nt;
+            for (int a = 0; a < nt; ++a)
+                for (int b = 0; b <= a; ++b) push2(s, (a & 0xffff) | (b << 16));
+        }
+        P.update_cb.cnt = ((int)tasks.size() - P.update_cb.off) / 2;
         P.fwd.off = (int)tasks.size();
         for (int s : sns)
             for (int a = 0; a * 64 < sn[s].m; ++a) push2(s, a);
@@ -676,6 +809,18 @@ int64_t CholBatch::device_bytes() const {
 }
 
 void CholBatch::factorize(const double* a_all, cudaStream_t st) {
+    // DOTGPU_FACTOR_TIMING=1: per-phase device times of this factorisation (CUDA events on the stream), printed to stderr
+    static const bool timing = std::getenv("DOTGPU_FACTOR_TIMING") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* tag) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(tag, e);
+    };
+    mark("start");
+    static const int potrf_dbg = std::getenv("DOTGPU_POTRF_DBG") ? std::atoi(std::getenv("DOTGPU_POTRF_DBG")) : 0;  // experiments only
     DG_CUDA(cudaMemsetAsync(L.p, 0, L.bytes(), st));
     DG_CUDA(cudaMemsetAsync(CB.p, 0, CB.bytes(), st));
     DG_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), st));
@@ -683,27 +828,37 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
         k_scatter_a<<<ceil_div(nnz_a_total, 256), 256, 0, st>>>(nnz_a_total, d_amap.p, a_all, L.p);
         count_launch();
     }
+    mark("memset+scatter");
     const int* T = d_tasks.p;
     for (int lv = 0; lv < nlevels; ++lv) {
         const LevelPlan& P = plan[lv];
         if (P.extend.cnt) {
             k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task2*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p);
             count_launch();
+            mark("extend_add");
         }
         for (size_t kb = 0; kb < P.potrf.size(); ++kb) {
             if (P.potrf[kb].cnt) {
                 k_potrf<<<P.potrf[kb].cnt, 256, POTRF_SMEM, st>>>(T + P.potrf[kb].off, (int)kb, d_sn.p, L.p, tinv.p,
-                                                                                 d_status.p);
+                                                                                 d_status.p, potrf_dbg);
                 count_launch();
+                mark("potrf");
             }
             if (P.trsm[kb].cnt) {
                 k_trsm<<<P.trsm[kb].cnt, 128, 0, st>>>((const Task2*)(T + P.trsm[kb].off), (int)kb, d_sn.p, L.p, tinv.p);
                 count_launch();
+                mark("trsm");
             }
             if (P.update[kb].cnt) {
                 k_update<<<P.update[kb].cnt, 128, 0, st>>>((const Task3*)(T + P.update[kb].off), (int)kb, d_sn.p, L.p, CB.p);
                 count_launch();
+                mark("update_panel");
             }
+        }
+        if (P.update_cb.cnt) {
+            k_update_cb<<<P.update_cb.cnt, 128, 0, st>>>((const Task3*)(T + P.update_cb.off), d_sn.p, L.p, CB.p);
+            count_launch();
+            mark("update_cb");
         }
     }
     // ---- solve panels ----
@@ -720,8 +875,28 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
         k_sp_below<<<sp_below.cnt, 128, 0, st>>>((const Task3*)(T + sp_below.off), d_sn.p, L.p, Sp.p);
         count_launch();
     }
+    mark("solve_panels");
     pack_panels(st);
+    mark("pack");
     factorized = true;
+    if (timing && !marks.empty()) {
+        cudaStreamSynchronize(st);
+        std::vector<std::pair<std::string, std::pair<double, int>>> agg;
+        double total = 0.0;
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            total += ms;
+            bool found = false;
+            for (auto& a : agg)
+                if (a.first == marks[i].first) { a.second.first += ms; a.second.second++; found = true; }
+            if (!found) agg.push_back({marks[i].first, {ms, 1}});
+        }
+        std::fprintf(stderr, "[dotgpu factorize] total %.3f ms:", total);
+        for (auto& a : agg) std::fprintf(stderr, " %s %.3f (%d)", a.first.c_str(), a.second.first, a.second.second);
+        std::fprintf(stderr, "\n");
+        for (auto& m : marks) cudaEventDestroy(m.second);
+    }
 }
 
 void CholBatch::check_status(cudaStream_t st) {

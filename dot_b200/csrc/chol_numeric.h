@@ -60,7 +60,7 @@ struct CholBatch {
 
     struct Span { int off = 0, cnt = 0; };
     struct LevelPlan {
-        Span extend, fwd, bwd;
+        Span extend, fwd, bwd, update_cb;
         std::vector<Span> potrf, trsm, update;  // per pivot step
     };
     std::vector<LevelPlan> plan;

@@ -218,6 +218,191 @@ void launch_dot(long long n, const double* a, const double* b, double* partial, 
     count_launch();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fused L-BFGS kernels
+constexpr int MD_TPB = 256;
+constexpr int MD_MAX_BLOCKS = 296;  // 2 CTAs per SM
+
+__global__ void __launch_bounds__(MD_TPB) k_dots(long long n, DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
+                                                 double* __restrict__ sc) {
+    __shared__ double sh[8];
+    __shared__ bool last;
+    double acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+    for (long long i = (long long)blockIdx.x * MD_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * MD_TPB) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+            if (j < P.n) acc[j] += P.a[j][i] * P.b[j][i];
+    }
+    for (int j = 0; j < P.n; ++j) {
+        double r = cta_sum256(acc[j], sh);
+        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int j = 0; j < P.n; ++j) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += MD_TPB) v += __ldcg(partial + (size_t)j * gridDim.x + i);
+        double tot = cta_sum256(v, sh);
+        if (threadIdx.x == 0) sc[P.out[j]] = tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+// compact first loop: xi_i = (s_i . q_i) / (y_i . s_i),  s_i . q_i = -(s_i . g) - sum_{j newer than i} xi_j (s_i . y_j)
+__device__ __forceinline__ void lbfgs_xi(const double* __restrict__ sc, const HistList& H, double* xi) {
+    for (int i = H.n - 1; i >= 0; --i) {
+        const int si = H.slot[i];
+        double v = -sc[SC_SG + si];
+        for (int j = H.n - 1; j > i; --j) v -= xi[j] * sc[SC_SY + 8 * si + H.slot[j]];
+        xi[i] = v / sc[SC_SY + 8 * si + si];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_lbfgs_q(long long n, double* __restrict__ q, const double* __restrict__ g, HistList H,
+                                                 double* __restrict__ sc) {
+    __shared__ double xi[LB_MAXH];
+    if (threadIdx.x == 0) {
+        lbfgs_xi(sc, H, xi);
+        if (blockIdx.x == 0)
+            for (int i = 0; i < H.n; ++i) sc[SC_XI + H.slot[i]] = xi[i];
+    }
+    __syncthreads();
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    double v = -g[e];
+    for (int i = H.n - 1; i >= 0; --i) v -= xi[i] * H.Y[i][e];
+    q[e] = v;
+}
+
+__global__ void __launch_bounds__(256) k_lbfgs_p(long long n, double* __restrict__ p, HistList H, double* __restrict__ sc) {
+    __shared__ double c[LB_MAXH];
+    if (threadIdx.x == 0) {
+        // compact second loop: beta_i = (y_i . p_i) / (y_i . s_i),  y_i . p_i = y_i . p0 + sum_{j older than i} c_j (y_i . s_j),  c_i = xi_i - beta_i
+        double pg = sc[SC_P0G];
+        for (int i = 0; i < H.n; ++i) {
+            const int si = H.slot[i];
+            double v = sc[SC_YP + si];
+            for (int j = 0; j < i; ++j) v += c[j] * sc[SC_SY + 8 * H.slot[j] + si];
+            c[i] = sc[SC_XI + si] - v / sc[SC_SY + 8 * si + si];
+            pg += c[i] * sc[SC_SG + si];
+        }
+        if (blockIdx.x == 0) sc[SC_PG] = pg;
+    }
+    __syncthreads();
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    double v = p[e];
+    for (int i = 0; i < H.n; ++i) v += c[i] * H.S[i][e];
+    p[e] = v;
+}
+
+__global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                                        const double* __restrict__ a, const double* __restrict__ p,
+                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    __shared__ double sh[8];
+    __shared__ bool last;
+    int i = blockIdx.x * 256 + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        const double pi = p[i];
+        int b = ia[i], e = ia[i + 1];
+        double off = 0.0;
+        for (int k = b + 1; k < e; ++k) off += a[k] * p[ja[k]];
+        s = pi * (a[b] * pi + 2.0 * off);  // first entry of every row is the diagonal
+    }
+    double r = cta_sum256(s, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = r;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 256) v += __ldcg(partial + k);
+    __syncthreads();
+    double tot = cta_sum256(v, sh);
+    if (threadIdx.x == 0) {
+        sc[SC_PHP] = tot;
+        sc[SC_ALPHA] = fmax(0.1, fmin(1.0, -sc[SC_PG] / tot));
+        *counter = 0u;
+    }
+}
+
+__global__ void k_axpy_dev(long long n, double* __restrict__ out, const double* __restrict__ x0, const double* __restrict__ p,
+                           const double* __restrict__ alpha_dev, double alpha_host) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double alpha = alpha_dev ? *alpha_dev : alpha_host;
+    if (i < n) out[i] = x0[i] + alpha * p[i];
+}
+
+__global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double* __restrict__ p, const double* __restrict__ gn,
+                                                      const double* __restrict__ go, double* __restrict__ Sn, double* __restrict__ Yn, int sl,
+                                                      const double* __restrict__ alpha_dev, double alpha_host, HistList H,
+                                                      double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    __shared__ double sh[8];
+    __shared__ bool last;
+    const double alpha = alpha_dev ? *alpha_dev : alpha_host;
+    double acc[2 + 2 * LB_MAXH];
+#pragma unroll
+    for (int j = 0; j < 2 + 2 * LB_MAXH; ++j) acc[j] = 0.0;
+    for (long long i = (long long)blockIdx.x * MD_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * MD_TPB) {
+        const double gnew = gn[i];
+        const double s = alpha * p[i], y = gnew - go[i];
+        if (Sn) {
+            Sn[i] = s;
+            Yn[i] = y;
+        }
+        acc[0] += gnew * gnew;
+        acc[1] += y * s;
+#pragma unroll
+        for (int j = 0; j < LB_MAXH; ++j)
+            if (j < H.n && Sn) {
+                acc[2 + 2 * j] += H.S[j][i] * y;
+                acc[3 + 2 * j] += s * H.Y[j][i];
+            }
+    }
+    const int nacc = Sn ? 2 + 2 * H.n : 2;
+    for (int j = 0; j < nacc; ++j) {
+        double r = cta_sum256(acc[j], sh);
+        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int j = 0; j < nacc; ++j) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += MD_TPB) v += __ldcg(partial + (size_t)j * gridDim.x + i);
+        double tot = cta_sum256(v, sh);
+        if (threadIdx.x == 0) {
+            if (j == 0) sc[SC_GG] = tot;
+            else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
+            else {
+                const int h = (j - 2) >> 1, sh_ = H.slot[h];
+                if ((j & 1) == 0) sc[SC_SY + 8 * sh_ + sl] = tot;  // s_h . y_new
+                else sc[SC_SY + 8 * sl + sh_] = tot;               // s_new . y_h
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
 #define EW_LAUNCH(kernel, n, ...)                                              \
     do {                                                                       \
         if ((n) > 0) {                                                         \
@@ -252,6 +437,34 @@ void launch_velocity(int nV, double* vel, const double* x, const double* xn, dou
     long long n = 3LL * nV;
     EW_LAUNCH(k_velocity, n, n, vel, x, xn, dt);
 }
+int multidot_partial_count() { return MD_MAX_BLOCKS * (2 + 2 * LB_MAXH); }
+static int md_blocks(long long n) { return (int)std::min<long long>(MD_MAX_BLOCKS, std::max<long long>(1, (n + MD_TPB * 4 - 1) / (MD_TPB * 4))); }
+
+void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
+    if (P.n <= 0) return;
+    k_dots<<<md_blocks(n), MD_TPB, 0, st>>>(n, P, partial, counter, sc);
+    count_launch();
+}
+void launch_lbfgs_q(long long n, double* q, const double* g, const HistList& H, double* sc, cudaStream_t st) {
+    EW_LAUNCH(k_lbfgs_q, n, n, q, g, H, sc);
+}
+void launch_lbfgs_p(long long n, double* p, const HistList& H, double* sc, cudaStream_t st) { EW_LAUNCH(k_lbfgs_p, n, n, p, H, sc); }
+void launch_quadform_alpha(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, unsigned* counter,
+                           double* sc, cudaStream_t st) {
+    k_quadform_alpha<<<ceil_div(n, 256), 256, 0, st>>>(n, ia, ja, a, p, partial, counter, sc);
+    count_launch();
+}
+void launch_axpy_dev(long long n, double* out, const double* x0, const double* p, const double* alpha_dev, double alpha_host,
+                     cudaStream_t st) {
+    EW_LAUNCH(k_axpy_dev, n, n, out, x0, p, alpha_dev, alpha_host);
+}
+void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
+                      const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
+                      cudaStream_t st) {
+    k_pair_dots<<<md_blocks(n), MD_TPB, 0, st>>>(n, p, g_new, g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc);
+    count_launch();
+}
+
 void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st) { EW_LAUNCH(k_gather, n, n, gidx, q, b); }
 void launch_scatter_avg(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, cudaStream_t st) {
     EW_LAUNCH(k_scatter_avg, ndof, ndof, cptr, cidx, xs, dup, p);

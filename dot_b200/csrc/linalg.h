@@ -46,6 +46,49 @@ void launch_xtilde(int nV, double* xt, const double* xn, const double* vel, cons
                    double gz, cudaStream_t st);
 void launch_velocity(int nV, double* vel, const double* x, const double* xn, double dt, cudaStream_t st);
 
+// ---- fused L-BFGS iteration kernels (compact two-loop recursion: all inner products of an iteration are taken in two
+// multi-dot passes against the Gram matrix of the history, DOTTimeStepper.cpp:389-398, 459-466 restated) ----
+constexpr int LB_MAXH = 8;
+struct HistList {            // active pairs, oldest -> newest, as buffer slots
+    int n;
+    int slot[LB_MAXH];
+    const double* S[LB_MAXH];  // by position
+    const double* Y[LB_MAXH];
+};
+struct DotPairs {
+    int n;
+    const double* a[12];
+    const double* b[12];
+    int out[12];             // index into the scalar array
+};
+// device scalar slots
+enum ScalarSlot {
+    SC_E = 0, SC_GG = 1, SC_PG = 2, SC_PHP = 3, SC_ALPHA = 4, SC_P0G = 5, SC_YS_NEW = 6, SC_DOT = 7,
+    SC_SG = 8,    // s_i . g      by slot
+    SC_YP = 16,   // y_i . p0     by slot
+    SC_XI = 24,   // first-loop coefficients by slot
+    SC_SY = 32,   // Gram matrix (s_i . y_j) at [SC_SY + 8*i + j], by slots
+    SC_COUNT = 96
+};
+int multidot_partial_count();
+// sc[P.out[j]] = a_j . b_j for all pairs in one pass (deterministic: fixed grid, block partials, last block adds them in order)
+void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st);
+// q = -g - sum_i xi_i y_i with xi from the compact first loop (needs sc[SC_SG+slot], sc[SC_SY..]); stores xi to sc[SC_XI+slot]
+void launch_lbfgs_q(long long n, double* q, const double* g, const HistList& H, double* sc, cudaStream_t st);
+// p = p0 + sum_i (xi_i - beta_i) s_i with beta from the compact second loop (needs sc[SC_YP+slot], sc[SC_P0G]); stores p.g to sc[SC_PG]
+void launch_lbfgs_p(long long n, double* p, const HistList& H, double* sc, cudaStream_t st);
+// sc[SC_PHP] = p^T A p and sc[SC_ALPHA] = clamp(-sc[SC_PG] / sc[SC_PHP], 0.1, 1)   (Optimizer::initStepSize, Optimizer.cpp:1076-1093)
+void launch_quadform_alpha(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, unsigned* counter,
+                           double* sc, cudaStream_t st);
+// out = x0 + alpha p with alpha read from the device (alpha_dev) or given (alpha_dev == nullptr)
+void launch_axpy_dev(long long n, double* out, const double* x0, const double* p, const double* alpha_dev, double alpha_host,
+                     cudaStream_t st);
+// new pair s = alpha p, y = g_new - g_old written to S_new / Y_new, and in the same pass: sc[SC_GG] = g_new.g_new,
+// sc[SC_SY + 8*sl + sl] = y.s, sc[SC_SY + 8*slot_i + sl] = s_i.y, sc[SC_SY + 8*sl + slot_i] = s.y_i
+void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
+                      const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
+                      cudaStream_t st);
+
 // ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
 // b[i] = q[gidx[i]]  for the concatenated permuted right-hand sides
 void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st);

@@ -212,6 +212,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     xperm.alloc(std::max<int64_t>(chol.n_total, 1));
     qf_partial.alloc(ceil_div((long long)n3, 256) + 1);
     dot_partial.alloc(dot_partial_count((long long)n3));
+    md_partial.alloc(multidot_partial_count());
     S.resize(cfg.history + 1);
     Y.resize(cfg.history + 1);
     for (int i = 0; i <= cfg.history; ++i) {
@@ -299,6 +300,21 @@ void Stepper::frame_resident(const int32_t* idx, const double* pos, int count, d
     frame_core(stats, false);
 }
 
+HistList Stepper::hist_list() const {
+    HistList H;
+    H.n = (int)hist.size();
+    for (int i = 0; i < LB_MAXH; ++i) {
+        H.slot[i] = 0;
+        H.S[i] = H.Y[i] = nullptr;
+    }
+    for (int i = 0; i < H.n; ++i) {
+        H.slot[i] = hist[i];
+        H.S[i] = S[hist[i]].p;
+        H.Y[i] = Y[hist[i]].p;
+    }
+    return H;
+}
+
 void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     const size_t n3 = 3 * (size_t)nV;
     const long long n = (long long)n3;
@@ -319,54 +335,60 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     std::vector<int> free_slots;
     for (int i = 0; i <= cfg.history; ++i) free_slots.push_back(i);
     do {
-        // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466) ----
-        k_neg<<<ceil_div(n, 256), 256, 0, st>>>(n, q.p, g.p);
-        count_launch();
-        for (int h = (int)hist.size() - 1; h >= 0; --h) {
-            int sl = hist[h];
-            launch_dot(n, S[sl].p, q.p, dot_partial.p, counter.p, sc.p + SC_DOT, st);
-            launch_lbfgs_first(n, q.p, Y[sl].p, sc.p, SC_DOT, SC_YS + sl, SC_KSI + sl, st);
+        // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466), compact form: the inner
+        //      products against the history are taken in two multi-dot passes, the recursions run on scalars ----
+        const HistList H = hist_list();
+        if (H.n > 0) {
+            DotPairs P;
+            P.n = H.n;
+            for (int i = 0; i < H.n; ++i) { P.a[i] = H.S[i]; P.b[i] = g.p; P.out[i] = SC_SG + H.slot[i]; }
+            launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
+        launch_lbfgs_q(n, q.p, g.p, H, sc.p, st);
         precondition_dev(q.p, p.p);
-        for (int h = 0; h < (int)hist.size(); ++h) {
-            int sl = hist[h];
-            launch_dot(n, Y[sl].p, p.p, dot_partial.p, counter.p, sc.p + SC_DOT, st);
-            launch_lbfgs_second(n, p.p, S[sl].p, sc.p, SC_DOT, SC_YS + sl, SC_KSI + sl, st);
+        {
+            DotPairs P;
+            P.n = H.n + 1;
+            for (int i = 0; i < H.n; ++i) { P.a[i] = H.Y[i]; P.b[i] = p.p; P.out[i] = SC_YP + H.slot[i]; }
+            P.a[H.n] = g.p; P.b[H.n] = p.p; P.out[H.n] = SC_P0G;
+            launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
-        // ---- initial step length (Optimizer.cpp:1076-1093) ----
-        launch_dot(n, p.p, g.p, dot_partial.p, counter.p, sc.p + SC_PG, st);
-        launch_quadform(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, sc.p + SC_PHP, st);
-        fetch_scalars(SC_PG, 2);
-        double alpha = std::max(0.1, std::min(1.0, -h_sc[SC_PG] / h_sc[SC_PHP]));
-        // ---- back-tracking line search (Optimizer.cpp:752-881) ----
+        launch_lbfgs_p(n, p.p, H, sc.p, st);
+        // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
+        launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
+        // ---- back-tracking line search (Optimizer.cpp:752-881): the first trial and everything that follows an accepted
+        //      step are enqueued without waiting; the host looks at the result once per iteration ----
         std::swap(x.p, x0.p);  // x0 = current positions
-        double Et;
-        while (true) {
-            launch_axpy(n, x.p, x0.p, p.p, alpha, st);
-            Et = energy_at(x.p);
-            ++evals;
-            if (Et > E && alpha > 0.0) {
+        launch_axpy_dev(n, x.p, x0.p, p.p, sc.p + SC_ALPHA, 0.0, st);
+        launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
+        ++evals;
+        gradient_at(x.p, g_old.p);  // gradient at the trial point (g_old is the spare buffer until the step is accepted)
+        const int sl = cfg.history > 0 ? free_slots.back() : -1;  // history+1 buffers: a candidate slot is always free
+        launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, sc.p + SC_ALPHA, 0.0, H,
+                         md_partial.p, counter.p, sc.p, st);
+        fetch_scalars(0, SC_COUNT);
+        double alpha = h_sc[SC_ALPHA], Et = h_sc[SC_E];
+        if (Et > E && alpha > 0.0) {
+            // rare: halve until the energy does not increase, then redo the gradient / pair at the accepted point
+            while (true) {
                 alpha /= 2.0;
                 ++halvings;
                 if (alpha == 0.0) break;
-            } else
-                break;
+                launch_axpy_dev(n, x.p, x0.p, p.p, nullptr, alpha, st);
+                Et = energy_at(x.p);
+                ++evals;
+                if (!(Et > E)) break;
+            }
+            gradient_at(x.p, g_old.p);
+            launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, nullptr, alpha, H, md_partial.p,
+                             counter.p, sc.p, st);
+            fetch_scalars(0, SC_COUNT);
         }
         E = Et;
-        // ---- history update (DOTTimeStepper.cpp:476-493) ----
         std::swap(g.p, g_old.p);
-        gradient_at(x.p, g.p);
-        launch_dot(n, g.p, g.p, dot_partial.p, counter.p, sc.p + SC_GG, st);
-        int sl = -1;
-        if (cfg.history > 0) {
-            sl = free_slots.back();  // history+1 buffers: a candidate slot is always free
-            launch_scale_copy(n, S[sl].p, p.p, alpha, st);
-            launch_sub(n, Y[sl].p, g.p, g_old.p, st);
-            launch_dot(n, Y[sl].p, S[sl].p, dot_partial.p, counter.p, sc.p + SC_YS + sl, st);
-        }
-        fetch_scalars(0, SC_COUNT);
         gg = h_sc[SC_GG];
-        if (sl >= 0 && h_sc[SC_YS + sl] > 0.0) {  // keep the pair iff y.s > 0, then drop the oldest beyond `history`
+        // ---- history update (DOTTimeStepper.cpp:476-493): keep the pair iff y.s > 0, then drop the oldest beyond `history` ----
+        if (sl >= 0 && h_sc[SC_YS_NEW] > 0.0) {
             free_slots.pop_back();
             hist.push_back(sl);
             if ((int)hist.size() > cfg.history) {

@@ -31,7 +31,8 @@ struct Stepper {
     DeviceFill fill;
     CholBatch chol;
     DevBuf<int> gidx, cptr, cidx, dup;
-    DevBuf<double> x, x0, xn, xt, vel, g, g_old, q, p, bperm, xperm, qf_partial, dot_partial;
+    DevBuf<double> x, x0, xn, xt, vel, g, g_old, q, p, bperm, xperm, qf_partial, dot_partial, md_partial;
+    HistList hist_list() const;
     std::vector<DevBuf<double>> S, Y;
     std::deque<int> hist;            // slots, oldest first
     DevBuf<double> sc;               // device scalars
@@ -65,6 +66,5 @@ struct Stepper {
     double time_kernels(int which, int reps);
 };
 
-enum ScalarSlot { SC_E = 0, SC_GG = 1, SC_PG = 2, SC_PHP = 3, SC_DOT = 4, SC_YS = 8, SC_KSI = 24, SC_COUNT = 48 };
 
 }  // namespace dotgpu
