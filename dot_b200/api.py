@@ -40,7 +40,8 @@ class StepperConfig(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("iters", C.c_int32), ("halvings", C.c_int32), ("energy_evals", C.c_int32), ("converged", C.c_int32),
                 ("E", C.c_double), ("grad_sqnorm", C.c_double), ("target", C.c_double), ("ms_total", C.c_double),
-                ("ms_solve", C.c_double), ("ms_refresh", C.c_double)]
+                ("ms_solve", C.c_double), ("ms_refresh", C.c_double), ("ms_precond", C.c_double), ("precond_calls", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 def lib():
@@ -93,6 +94,16 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _chk(lib().dotgpu_nccl_unique_id(buf))
     return buf.raw
+
+
+def owned_subdomains(k, rank, world):
+    """Subdomain ids rank `rank` of `world` factors and solves (the multi-GPU sharding of the path)."""
+    n = lib().dotgpu_owned_subdomains(int(k), int(rank), int(world), None)
+    if n < 0:
+        raise DotGpuError(n, "bad rank/world")
+    out = np.empty(n, dtype=np.int32)
+    lib().dotgpu_owned_subdomains(int(k), int(rank), int(world), _p(out))
+    return out
 
 
 def mesh_features(V_rest, tets, YM=1e5, PR=0.4, rho=1000.0):

@@ -104,6 +104,14 @@ int dotgpu_device_count(void) {
     return n;
 }
 
+int dotgpu_owned_subdomains(int num_subdomains, int rank, int world, int32_t* out) {
+    if (num_subdomains < 1 || world < 1 || rank < 0 || rank >= world) return DOTGPU_ERR_INVALID;
+    const std::vector<int> o = owned_subdomains(num_subdomains, rank, world);
+    if (out)
+        for (size_t i = 0; i < o.size(); ++i) out[i] = o[i];
+    return (int)o.size();
+}
+
 int dotgpu_mesh_features(int nV, int nT, const double* V_rest, const int32_t* tets, double YM, double PR, double rho,
                          double* DmInv_out, double* vol_out, double* mass_out, double* mu_out, double* lambda_out) {
     API_BEGIN

@@ -34,6 +34,7 @@ Stepper::~Stepper() {
     if (h_x) cudaFreeHost(h_x);
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : pc_ev) cudaEventDestroy(e);
     comm.reset();
     if (st) cudaStreamDestroy(st);
 }
@@ -117,12 +118,8 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     // ---- domain decomposition, owned subdomains ----
     const int k = cfg.num_subdomains;
     std::vector<char> mask(k, 0);
-    owned.clear();
-    for (int s = 0; s < k; ++s)
-        if (s % cfg.world == cfg.rank) {
-            mask[s] = 1;
-            owned.push_back(s);
-        }
+    owned = owned_subdomains(k, cfg.rank, cfg.world);
+    for (int s : owned) mask[s] = 1;
     dd.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), V_rest.data(), cfg.rho, mass_h.data(), true, &mask);
 
     // ---- concatenated matrices: [global | owned subdomains] ----
@@ -345,7 +342,16 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
             launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
         launch_lbfgs_q(n, q.p, g.p, H, sc.p, st);
+        if (pc_ev.size() < 2 * (size_t)(iters + 1)) {
+            cudaEvent_t a, b;
+            DG_CUDA(cudaEventCreate(&a));
+            DG_CUDA(cudaEventCreate(&b));
+            pc_ev.push_back(a);
+            pc_ev.push_back(b);
+        }
+        DG_CUDA(cudaEventRecord(pc_ev[2 * iters], st));
         precondition_dev(q.p, p.p);
+        DG_CUDA(cudaEventRecord(pc_ev[2 * iters + 1], st));
         {
             DotPairs P;
             P.n = H.n + 1;
@@ -427,6 +433,15 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         stats->ms_total = a;
         stats->ms_solve = b;
         stats->ms_refresh = c;
+        double pc = 0.0;
+        for (int i = 0; i < iters; ++i) {
+            float t = 0;
+            cudaEventElapsedTime(&t, pc_ev[2 * i], pc_ev[2 * i + 1]);
+            pc += t;
+        }
+        stats->ms_precond = pc;
+        stats->precond_calls = iters;
+        stats->pad_ = 0;
     }
 }
 

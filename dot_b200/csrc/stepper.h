@@ -15,6 +15,14 @@ namespace dotgpu {
 
 struct Comm;  // NCCL communicator wrapper (comm.cpp)
 
+// subdomains are dealt round-robin to ranks (every rank factors / solves its own ones)
+inline std::vector<int> owned_subdomains(int k, int rank, int world) {
+    std::vector<int> o;
+    for (int s = 0; s < k; ++s)
+        if (s % world == rank) o.push_back(s);
+    return o;
+}
+
 struct Stepper {
     dotgpu_stepper_config cfg;
     int nV = 0, nT = 0;
@@ -44,6 +52,7 @@ struct Stepper {
     std::vector<double> iter_log;    // (alpha, E, |g|^2) rows
     int64_t launches0 = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> pc_ev;  // event pairs around the preconditioner applications of a frame
     std::unique_ptr<Comm> comm;
     DevBuf<unsigned char> own_tet;   // multi-GPU: 1 if this rank sums the tet into energy/gradient
 

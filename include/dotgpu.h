@@ -172,6 +172,9 @@ typedef struct dotgpu_stepper_config {
     int32_t flags;            /* bit0: use CUDA graphs */
 } dotgpu_stepper_config;
 void dotgpu_stepper_default_config(dotgpu_stepper_config* c);
+/* Static map of subdomains to ranks (the multi-GPU sharding of the path): writes the ascending list of
+ * subdomain ids rank `rank` of `world` factors and solves; returns their number (or a negative error code).  out may be NULL. */
+int dotgpu_owned_subdomains(int num_subdomains, int rank, int world, int32_t* out);
 /* rank 0 calls this and broadcasts the 128 bytes (e.g. torch.distributed) before every rank creates its stepper */
 int dotgpu_nccl_unique_id(void* out128);
 
@@ -182,6 +185,8 @@ typedef struct dotgpu_frame_stats {
     int32_t converged;        /* 1 if ||g||^2 <= targetGRes */
     double E, grad_sqnorm, target;
     double ms_total, ms_solve, ms_refresh;  /* device times (CUDA events) */
+    double ms_precond;        /* device time of the preconditioner applications (K5) of this frame, CUDA events on the stepper's stream */
+    int32_t precond_calls, pad_;
 } dotgpu_frame_stats;
 
 /* Builds everything precompute() builds: mesh features, DD from labels, patterns, symbolic analysis of
