@@ -116,6 +116,15 @@ def run_reference(wl, steps, warmup, threads=None):
             "timers_sec": st["timers_sec"], "sumV": st["sumV"]}
 
 
+def _emit(line):
+    """Exactly one JSON line on the real stdout (libraries such as NCCL print banners to fd 1: it is parked on stderr meanwhile)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,7 +152,7 @@ def main():
             return 0
         r = run_reference(wl, a.steps, a.warmup)
         if r is None or "error" in r:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/dot_ref missing or failed: %s" % (r or {}).get("error", "not built")}))
+            _emit({"impl": "reference", "unavailable": "oracle/_ref/dot_ref missing or failed: %s" % (r or {}).get("error", "not built")})
             return 0
         line = {"metric": "simulated frames/sec (Newton-converged)", "value": r["fps"], "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": 1e3 * r["sec_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -152,22 +161,26 @@ def main():
                                  "sample": "frames %d..%d of the same run, unmodified reference (OpenMP shim for TBB, CHOLMOD 3.0.12, OpenBLAS 1 thread/solver)" % (a.warmup + 1, a.warmup + a.steps),
                                  "inner_iters": r["inner_iters"], "timers_sec": r["timers_sec"]},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     import torch
     import dot_b200 as D
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    nccl_id = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def fresh_nccl_id():
+        """Every communicator needs its own ncclUniqueId: rank 0 creates one, torch.distributed broadcasts the 128 bytes."""
+        if world == 1:
+            return None
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(D.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        torch.distributed.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,7 +194,7 @@ def main():
 
     def make():
         return D.Stepper(wl["V"], wl["T"], wl["epart"], fm, energy=wl["energy"], k=wl["k"], dt=DT, device=local_rank, rank=rank, world=world,
-                         nccl_id=nccl_id)
+                         nccl_id=fresh_nccl_id())
 
     # ---------------- value: resident positions ----------------
     t_setup = time.time()
@@ -310,7 +323,9 @@ def main():
             "nnz_L": nnz_l, "factor_flops": flops}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    _emit(line)
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 

@@ -3,8 +3,9 @@
 //   tets     int4[nT]            one 16-B load per thread
 //   DmInv    double[9][nT]       SoA -> coalesced across a warp of tets
 //   vol,mu,lam double[nT]
-//   vf_ptr/vf_idx                CSR of vFLoc: per vertex, ascending (tet*4+corner)  (Mesh.cpp:606-611)
-//   ge       double[12][nT]      elemental gradients (SoA), scratch
+//   lv_ptr/g_cptr/g_cidx/vp_*    K2 tables: CTA-local vertex lists and per-vertex partial lists (ascending tet order,
+//                                the order of Mesh.cpp:606-611 / Energy.cpp:543-563 up to the association into CTA partials)
+//   gpart    double[3][#(CTA,vertex)]  per-CTA vertex partial gradients, scratch
 //   He       double[nT][16][9]   elemental Hessians as 4x4 blocks of 3x3 (72 contiguous bytes per block)
 #pragma once
 #include "common.h"
@@ -18,8 +19,10 @@ struct DeviceMesh {
     DevBuf<double> vol, mu, lam;
     DevBuf<double> mass;    // nV (may be empty for the bare energy object)
     DevBuf<unsigned char> fixed;  // nV
-    DevBuf<int> vf_ptr, vf_idx;
-    DevBuf<double> ge;      // 12*nT
+    // K2 tables (static): per CTA of 128 tets the distinct vertices and their (tet, corner) lists; per vertex its partials
+    DevBuf<int> lv_ptr, vp_ptr, vp_idx;
+    DevBuf<unsigned short> g_cptr, g_cidx;
+    DevBuf<double> gpart;   // 3 doubles per (CTA, local vertex)
     DevBuf<double> He;      // 144*nT, allocated on first use
     DevBuf<double> partial; // block partial sums for reductions
     int n_partial = 0;

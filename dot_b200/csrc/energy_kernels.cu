@@ -3,6 +3,8 @@
 // (3*nV doubles are L2-resident for every mesh this path targets).  Reductions are deterministic
 // (fixed-shape block tree + a single-CTA final pass); the vertex gather sums elemental
 // contributions in ascending tet order like Energy.cpp:543-563.
+#include <algorithm>
+
 #include "device_mesh.h"
 #include "elastic.cuh"
 
@@ -75,20 +77,20 @@ __global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const i
     __shared__ double sh[TPB / 32];
     __shared__ bool last;
     double e = 0.0;
-    if ((int)blockIdx.x < nbT) {
-        int t = blockIdx.x * TPB + threadIdx.x;
-        if (t < nT) {
+    if ((int)blockIdx.x < nbT) {  // grid-stride over the tets: a bounded number of partials keeps the final pass short
+        for (int t = blockIdx.x * TPB + threadIdx.x; t < nT; t += nbT * TPB) {
             TetIn in;
             load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
-            e = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
-            if (per_elem) per_elem[t] = e;
+            const double et = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
+            if (per_elem) per_elem[t] = et;
+            e += et;
         }
     } else {
-        int v = (blockIdx.x - nbT) * TPB + threadIdx.x;
-        if (v < nV) {
+        const int nbV = gridDim.x - nbT;
+        for (int v = (blockIdx.x - nbT) * TPB + threadIdx.x; v < nV; v += nbV * TPB) {
             double a = x[3 * (size_t)v] - xt[3 * (size_t)v], b = x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1],
                    c = x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2];
-            e = (a * a + b * b + c * c) * mass[v] / 2.0;
+            e += (a * a + b * b + c * c) * mass[v] / 2.0;
         }
     }
     double s = block_sum<TPB>(e, sh);
@@ -115,54 +117,74 @@ __global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const i
     }
 }
 
+// K2, stage 1: elemental gradients of TPB tets, summed per vertex INSIDE the CTA before anything goes to memory.
+// The mesh is static, so the host precomputed per CTA the sorted list of distinct vertices its tets touch and, per such
+// local vertex, the (tet, corner) pairs that land on it (ascending): thread j adds them up from shared memory in that fixed
+// order and writes ONE 24-byte partial per (CTA, vertex) instead of 96 bytes per tet.  Deterministic, no atomics.
 template <int EN>
-__global__ void __launch_bounds__(TPB) k_elem_grad(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
-                                                   const double* __restrict__ vol, const double* __restrict__ mu,
-                                                   const double* __restrict__ lam, const double* __restrict__ x, double coef,
-                                                   double* __restrict__ ge) {
-    int t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= nT) return;
-    TetIn in;
-    load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
-    Mat3 P;
-    double psi;
-    first_piola<EN>(in.F, in.mu, in.lam, P, psi);
-    double w = coef * in.vol;
-    // g_e[3+3a+b] = w * Dm^-1.row(a) . P.row(b)   (IglUtils.cpp:857-868)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+__global__ void __launch_bounds__(TPB) k_grad_block(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+                                                    const double* __restrict__ vol, const double* __restrict__ mu,
+                                                    const double* __restrict__ lam, const double* __restrict__ x, double coef,
+                                                    const int* __restrict__ lv_ptr, const unsigned short* __restrict__ cptr,
+                                                    const unsigned short* __restrict__ cidx, double* __restrict__ part) {
+    __shared__ double sg[12 * TPB];
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    if (t < nT) {
+        TetIn in;
+        load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+        Mat3 P;
+        double psi;
+        first_piola<EN>(in.F, in.mu, in.lam, P, psi);
+        const double w = coef * in.vol;
+        // g_e[3+3a+b] = w * Dm^-1.row(a) . P.row(b)   (IglUtils.cpp:857-868); corner 0 = -(sum of the others)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        double g0 = w * (in.B[3 * a] * P(0, 0) + in.B[3 * a + 1] * P(0, 1) + in.B[3 * a + 2] * P(0, 2));
-        double g1 = w * (in.B[3 * a] * P(1, 0) + in.B[3 * a + 1] * P(1, 1) + in.B[3 * a + 2] * P(1, 2));
-        double g2 = w * (in.B[3 * a] * P(2, 0) + in.B[3 * a + 1] * P(2, 1) + in.B[3 * a + 2] * P(2, 2));
-        ge[(size_t)(3 + 3 * a) * nT + t] = g0;
-        ge[(size_t)(4 + 3 * a) * nT + t] = g1;
-        ge[(size_t)(5 + 3 * a) * nT + t] = g2;
-        s0 += g0; s1 += g1; s2 += g2;
+        for (int a = 0; a < 3; ++a) {
+            const double g0 = w * (in.B[3 * a] * P(0, 0) + in.B[3 * a + 1] * P(0, 1) + in.B[3 * a + 2] * P(0, 2));
+            const double g1 = w * (in.B[3 * a] * P(1, 0) + in.B[3 * a + 1] * P(1, 1) + in.B[3 * a + 2] * P(1, 2));
+            const double g2 = w * (in.B[3 * a] * P(2, 0) + in.B[3 * a + 1] * P(2, 1) + in.B[3 * a + 2] * P(2, 2));
+            sg[(3 + 3 * a) * TPB + threadIdx.x] = g0;
+            sg[(4 + 3 * a) * TPB + threadIdx.x] = g1;
+            sg[(5 + 3 * a) * TPB + threadIdx.x] = g2;
+            s0 += g0; s1 += g1; s2 += g2;
+        }
+        sg[threadIdx.x] = -s0;
+        sg[TPB + threadIdx.x] = -s1;
+        sg[2 * TPB + threadIdx.x] = -s2;
     }
-    ge[t] = -s0;
-    ge[(size_t)nT + t] = -s1;
-    ge[(size_t)2 * nT + t] = -s2;
+    __syncthreads();
+    const int p0 = lv_ptr[blockIdx.x], nl = lv_ptr[blockIdx.x + 1] - p0;
+    const unsigned short* __restrict__ cp = cptr + p0 + blockIdx.x;          // nl + 1 entries per CTA
+    const unsigned short* __restrict__ ci = cidx + (size_t)blockIdx.x * 4 * TPB;
+    for (int j = threadIdx.x; j < nl; j += TPB) {
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        for (int e = cp[j]; e < cp[j + 1]; ++e) {
+            const int code = ci[e], i = code >> 2, k = code & 3;
+            g0 += sg[(3 * k) * TPB + i];
+            g1 += sg[(3 * k + 1) * TPB + i];
+            g2 += sg[(3 * k + 2) * TPB + i];
+        }
+        double* __restrict__ o = part + 3 * (size_t)(p0 + j);
+        o[0] = g0; o[1] = g1; o[2] = g2;
+    }
 }
 
-__global__ void __launch_bounds__(256) k_vertex_gather(int nV, int nT, const int* __restrict__ vf_ptr, const int* __restrict__ vf_idx,
-                                                       const double* __restrict__ ge, const unsigned char* __restrict__ fixed,
-                                                       const double* __restrict__ x, const double* __restrict__ xt,
-                                                       const double* __restrict__ mass, double* __restrict__ g) {
+// K2, stage 2: per vertex, add the CTA partials (ascending CTA = ascending tet order), the inertia term m (x - xTilde)
+// (Optimizer.cpp:1239-1252), zero the Dirichlet vertices (Energy.cpp:561).
+__global__ void __launch_bounds__(256) k_grad_vertex(int nV, const int* __restrict__ vp_ptr, const int* __restrict__ vp_idx,
+                                                     const double* __restrict__ part, const unsigned char* __restrict__ fixed,
+                                                     const double* __restrict__ x, const double* __restrict__ xt,
+                                                     const double* __restrict__ mass, double* __restrict__ g) {
     int v = blockIdx.x * 256 + threadIdx.x;
     if (v >= nV) return;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (!fixed[v]) {
-        int b = vf_ptr[v], e = vf_ptr[v + 1];
-        for (int i = b; i < e; ++i) {
-            int code = vf_idx[i];
-            int t = code >> 2, k = code & 3;
-            g0 += ge[(size_t)(3 * k) * nT + t];
-            g1 += ge[(size_t)(3 * k + 1) * nT + t];
-            g2 += ge[(size_t)(3 * k + 2) * nT + t];
+        for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
+            const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
+            g0 += p[0]; g1 += p[1]; g2 += p[2];
         }
-        if (xt) {  // Optimizer.cpp:1239-1252
-            double m = mass[v];
+        if (xt) {
+            const double m = mass[v];
             g0 += m * (x[3 * (size_t)v] - xt[3 * (size_t)v]);
             g1 += m * (x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1]);
             g2 += m * (x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2]);
@@ -272,16 +294,44 @@ void DeviceMesh::init(int energy_type, int nV_, int nT_, const int32_t* tets_h, 
     std::vector<unsigned char> fx(nV, 0);
     if (fixed_h) fx.assign(fixed_h, fixed_h + nV);
     fixed.upload(fx, st);
-    // vFLoc as CSR, ascending tet (Mesh.cpp:606-611)
-    std::vector<int> ptr(nV + 1, 0);
-    for (size_t i = 0; i < (size_t)4 * nT; ++i) ptr[tets_h[i] + 1]++;
-    for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
-    std::vector<int> idx((size_t)4 * nT), cur(ptr.begin(), ptr.end() - 1);
-    for (int t = 0; t < nT; ++t)
-        for (int k = 0; k < 4; ++k) idx[cur[tets_h[4 * t + k]]++] = 4 * t + k;
-    vf_ptr.upload(ptr, st);
-    vf_idx.upload(idx, st);
-    ge.alloc((size_t)12 * nT);
+    // K2 tables: per CTA of TPB tets the distinct vertices (ascending) and their (tet, corner) lists; per vertex the partials
+    {
+        const int nb = ceil_div(nT, TPB);
+        std::vector<int> lvp(nb + 1, 0), lvv;
+        std::vector<unsigned short> cp, ci((size_t)nb * 4 * TPB, 0);
+        std::vector<std::pair<int, int>> corners;  // (vertex, code)
+        for (int b = 0; b < nb; ++b) {
+            corners.clear();
+            const int t0 = b * TPB, t1 = std::min(nT, t0 + TPB);
+            for (int t = t0; t < t1; ++t)
+                for (int k = 0; k < 4; ++k) corners.emplace_back(tets_h[4 * (size_t)t + k], 4 * (t - t0) + k);
+            std::sort(corners.begin(), corners.end());  // by vertex, then ascending (tet, corner)
+            int nl = 0;
+            for (size_t e = 0; e < corners.size(); ++e) {
+                if (e == 0 || corners[e].first != corners[e - 1].first) {
+                    cp.push_back((unsigned short)e);
+                    lvv.push_back(corners[e].first);
+                    ++nl;
+                }
+                ci[(size_t)b * 4 * TPB + e] = (unsigned short)corners[e].second;
+            }
+            cp.push_back((unsigned short)corners.size());
+            lvp[b + 1] = lvp[b] + nl;
+        }
+        const int npart = lvp[nb];
+        std::vector<int> vptr(nV + 1, 0), vidx(npart);
+        for (int i = 0; i < npart; ++i) vptr[lvv[i] + 1]++;
+        for (int v = 0; v < nV; ++v) vptr[v + 1] += vptr[v];
+        std::vector<int> cur(vptr.begin(), vptr.end() - 1);
+        for (int i = 0; i < npart; ++i) vidx[cur[lvv[i]]++] = i;  // ascending partial index = ascending CTA
+        lv_ptr.upload(lvp, st);
+        g_cptr.upload(cp, st);
+        g_cidx.upload(ci, st);
+        vp_ptr.upload(vptr, st);
+        if (vidx.empty()) vidx.push_back(0);
+        vp_idx.upload(vidx, st);
+        gpart.alloc(3 * (size_t)std::max(npart, 1));
+    }
     n_partial = ceil_div(nT, TPB) + ceil_div(nV, TPB);
     partial.alloc(n_partial);
     counter.alloc(1);
@@ -304,22 +354,23 @@ void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
     } while (0)
 
 void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st) {
-    const int nbT = ceil_div(m.nT, TPB), nbV = xTilde ? ceil_div(m.nV, TPB) : 0;
+    // at most 12 tet CTAs + 2 inertia CTAs per SM (148 SMs): <= 2072 partials for the last block
+    const int nbT = std::min(ceil_div(m.nT, TPB), 148 * 12), nbV = xTilde ? std::min(ceil_div(m.nV, TPB), 148 * 2) : 0;
     DISPATCH_EN(m, k_energy, nbT + nbV, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, xTilde,
                 m.mass.p, coef, m.partial.p, m.counter.p, E_out, (double*)nullptr);
 }
 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st) {
-    const int nbT = ceil_div(m.nT, TPB);
+    const int nbT = std::min(ceil_div(m.nT, TPB), 148 * 12);
     DISPATCH_EN(m, k_energy, nbT, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
                 (const double*)nullptr, (const double*)nullptr, 1.0, (double*)nullptr, (unsigned*)nullptr, (double*)nullptr, out);
 }
 
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st) {
     int nb = ceil_div(m.nT, TPB);
-    DISPATCH_EN(m, k_elem_grad, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.ge.p);
-    k_vertex_gather<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.nT, m.vf_ptr.p, m.vf_idx.p, m.ge.p, m.fixed.p, x, xTilde,
-                                                         m.mass.p, g);
+    DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p);
+    k_grad_vertex<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g);
     count_launch();
 }
 
