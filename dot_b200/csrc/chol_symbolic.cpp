@@ -188,20 +188,80 @@ void Symbolic::analyze(int n_, const int32_t* ia, const int32_t* ja, int leaf_no
             nd.order(S);
         }
     }
-    nsuper = (int)nd.supers.size();
-    // ---- numbering ----
-    std::vector<int> newnode(nn, -1), snode_of_node(nn, -1), node_ptr(nsuper + 1, 0);
-    {
+    // ---- node-level structure of a supernode list: numbering, below-row sets, supernodal etree ----
+    std::vector<int> newnode(nn, -1), snode_of_node(nn, -1), node_ptr, snode_of_newnode(nn);
+    std::vector<std::vector<int>> rown;
+    auto structure = [&](const std::vector<std::vector<int>>& supers) {
+        const int ns_ = (int)supers.size();
+        node_ptr.assign(ns_ + 1, 0);
         int c = 0;
-        for (int s = 0; s < nsuper; ++s) {
-            for (int v : nd.supers[s]) {
+        for (int s = 0; s < ns_; ++s) {
+            for (int v : supers[s]) {
                 newnode[v] = c++;
                 snode_of_node[v] = s;
             }
             node_ptr[s + 1] = c;
         }
         if (c != nn) throw std::logic_error("ordering lost nodes");
+        for (int v = 0; v < nn; ++v) snode_of_newnode[newnode[v]] = snode_of_node[v];
+        rown.assign(ns_, std::vector<int>());
+        std::vector<std::vector<int>> pending(ns_);
+        parent.assign(ns_, -1);
+        std::vector<int> mark(nn, -1);
+        for (int s = 0; s < ns_; ++s) {
+            std::vector<int>& r = rown[s];
+            const int last = node_ptr[s + 1] - 1;
+            for (int v : supers[s]) {
+                for (int i = g.ptr[v]; i < g.ptr[v + 1]; ++i) {
+                    int w = newnode[g.idx[i]];
+                    if (w > last && mark[w] != s) {
+                        mark[w] = s;
+                        r.push_back(w);
+                    }
+                }
+            }
+            for (int w : pending[s])
+                if (w > last && mark[w] != s) {
+                    mark[w] = s;
+                    r.push_back(w);
+                }
+            std::vector<int>().swap(pending[s]);
+            std::sort(r.begin(), r.end());
+            if (!r.empty()) {
+                int p = snode_of_newnode[r[0]];
+                parent[s] = p;
+                const int plast = node_ptr[p + 1] - 1;
+                for (int w : r)
+                    if (w > plast) pending[p].push_back(w);
+            }
+        }
+    };
+    // ---- chain amalgamation without fill: an only child whose update rows are exactly its parent's front (columns + rows)
+    //      forms one dense supernode with it (CHOLMOD's fundamental-supernode rule, cholmod_super_symbolic.c:393-458).  Every
+    //      merge removes one dependent level from the factorisation and from both solve sweeps. ----
+    for (;;) {
+        structure(nd.supers);
+        const int ns_ = (int)nd.supers.size();
+        std::vector<int> nchild(ns_, 0);
+        for (int s = 0; s < ns_; ++s)
+            if (parent[s] >= 0) nchild[parent[s]]++;
+        bool merged = false;
+        std::vector<std::vector<int>> out;
+        out.reserve(ns_);
+        for (int s = 0; s < ns_; ++s) {
+            const int p = parent[s];
+            if (p == s + 1 && nchild[p] == 1 &&
+                rown[s].size() == nd.supers[p].size() + rown[p].size()) {
+                nd.supers[p].insert(nd.supers[p].begin(), nd.supers[s].begin(), nd.supers[s].end());
+                merged = true;  // s disappears into p; p may merge further in the next pass
+            } else {
+                out.push_back(std::move(nd.supers[s]));
+            }
+        }
+        nd.supers.swap(out);
+        if (!merged) break;
     }
+    nsuper = (int)nd.supers.size();
     perm.resize(n);
     iperm.resize(n);
     for (int v = 0; v < nn; ++v)
@@ -211,39 +271,6 @@ void Symbolic::analyze(int n_, const int32_t* ia, const int32_t* ja, int leaf_no
         }
     super_ptr.resize(nsuper + 1);
     for (int s = 0; s <= nsuper; ++s) super_ptr[s] = B * node_ptr[s];
-    std::vector<int> snode_of_newnode(nn);
-    for (int v = 0; v < nn; ++v) snode_of_newnode[newnode[v]] = snode_of_node[v];
-    // ---- node-level row structures, supernodal etree ----
-    std::vector<std::vector<int>> rown(nsuper), pending(nsuper);
-    parent.assign(nsuper, -1);
-    std::vector<int> mark(nn, -1);
-    for (int s = 0; s < nsuper; ++s) {
-        std::vector<int>& r = rown[s];
-        const int last = node_ptr[s + 1] - 1;
-        for (int v : nd.supers[s]) {
-            for (int i = g.ptr[v]; i < g.ptr[v + 1]; ++i) {
-                int w = newnode[g.idx[i]];
-                if (w > last && mark[w] != s) {
-                    mark[w] = s;
-                    r.push_back(w);
-                }
-            }
-        }
-        for (int w : pending[s])
-            if (w > last && mark[w] != s) {
-                mark[w] = s;
-                r.push_back(w);
-            }
-        std::vector<int>().swap(pending[s]);
-        std::sort(r.begin(), r.end());
-        if (!r.empty()) {
-            int p = snode_of_newnode[r[0]];
-            parent[s] = p;
-            const int plast = node_ptr[p + 1] - 1;
-            for (int w : r)
-                if (w > plast) pending[p].push_back(w);
-        }
-    }
     // ---- expand to scalar rows ----
     row_ptr.assign(nsuper + 1, 0);
     for (int s = 0; s < nsuper; ++s)

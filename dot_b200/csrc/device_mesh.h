@@ -38,6 +38,11 @@ void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st);
 // g = gather(elemental gradients) [+ m (x - xTilde) on free vertices]; fixed entries zero
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st);
+// gradient + new L-BFGS pair + every inner product of the next iteration's first loop in one pass (see k_grad_vertex_pair)
+struct HistList;
+void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
+                          const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
+                          const HistList& H, double* partial, unsigned* counter, double* sc, cudaStream_t st);
 void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st);
 // fills m.He ([nT][16][9])
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st);

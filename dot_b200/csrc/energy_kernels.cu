@@ -6,6 +6,8 @@
 #include <algorithm>
 
 #include "device_mesh.h"
+#include "linalg.h"
+#include "reduce.cuh"
 #include "elastic.cuh"
 
 namespace dotgpu {
@@ -195,6 +197,76 @@ __global__ void __launch_bounds__(256) k_grad_vertex(int nV, const int* __restri
     g[3 * (size_t)v + 2] = g2;
 }
 
+// K2 stage 2 fused with the L-BFGS pair update (DOTTimeStepper.cpp:476-493): besides g_new it forms s = alpha p and
+// y = g_new - g_old, and takes every inner product the NEXT iteration needs in the same pass:
+//   |g_new|^2, y.s, s_i.y, s.y_i (Gram matrix row/column of the new pair) and s_i.g_new, s.g_new (first multi-dot of the next iteration)
+// Deterministic: fixed grid, block partials, last block adds them in order.
+__global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __restrict__ vp_ptr, const int* __restrict__ vp_idx,
+                                                          const double* __restrict__ part, const unsigned char* __restrict__ fixed,
+                                                          const double* __restrict__ x, const double* __restrict__ xt,
+                                                          const double* __restrict__ mass, double* __restrict__ g,
+                                                          const double* __restrict__ pdir, const double* __restrict__ g_old,
+                                                          double* __restrict__ Sn, double* __restrict__ Yn, int sl,
+                                                          const double* __restrict__ alpha_dev, double alpha_host, HistList H,
+                                                          double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    constexpr int NACC = 3 + 3 * LB_MAXH;  // gg, ys, s.g, then per history pair: s_i.y, s.y_i, s_i.g
+    __shared__ double shm[8 * NACC], res[NACC];
+    __shared__ bool last;
+    const double alpha = alpha_dev ? *alpha_dev : alpha_host;
+    double acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < nV; v += gridDim.x * 256) {
+        double gv[3] = {0.0, 0.0, 0.0};
+        if (!fixed[v]) {
+            for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
+                const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
+                gv[0] += p[0]; gv[1] += p[1]; gv[2] += p[2];
+            }
+            const double m = mass[v];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gv[c] += m * (x[3 * (size_t)v + c] - xt[3 * (size_t)v + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t e = 3 * (size_t)v + c;
+            const double gn = gv[c];
+            g[e] = gn;
+            const double s = alpha * pdir[e], y = gn - g_old[e];
+            if (Sn) {
+                Sn[e] = s;
+                Yn[e] = y;
+            }
+            acc[0] += gn * gn;
+            acc[1] += y * s;
+            acc[2] += s * gn;
+#pragma unroll
+            for (int j = 0; j < LB_MAXH; ++j)
+                if (j < H.n) {
+                    const double si = H.S[j][e];
+                    acc[3 + 3 * j] += si * y;
+                    acc[4 + 3 * j] += s * H.Y[j][e];
+                    acc[5 + 3 * j] += si * gn;
+                }
+        }
+    }
+    const int nacc = 3 + 3 * H.n;
+    if (!multi_reduce_256<NACC>(acc, nacc, shm, res, &last, partial, counter)) return;
+    if ((int)threadIdx.x < nacc) {
+        const int j = threadIdx.x;
+        const double tot = res[j];
+        if (j == 0) sc[SC_GG] = tot;
+        else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
+        else if (j == 2) { if (sl >= 0) sc[SC_SG + sl] = tot; }
+        else {
+            const int h = (j - 3) / 3, kind = (j - 3) % 3, sh_ = H.slot[h];
+            if (kind == 0) { if (sl >= 0) sc[SC_SY + 8 * sh_ + sl] = tot; }       // s_h . y_new
+            else if (kind == 1) { if (sl >= 0) sc[SC_SY + 8 * sl + sh_] = tot; }  // s_new . y_h
+            else sc[SC_SG + sh_] = tot;                                             // s_h . g_new
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_svd(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
                                              const double* __restrict__ vol, const double* __restrict__ mu,
                                              const double* __restrict__ lam, const double* __restrict__ x, double* Fo, double* Uo,
@@ -371,6 +443,17 @@ void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, doubl
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
                 m.g_cptr.p, m.g_cidx.p, m.gpart.p);
     k_grad_vertex<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g);
+    count_launch();
+}
+
+void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
+                          const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
+                          const HistList& H, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
+    int nb = ceil_div(m.nT, TPB);
+    DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p);
+    k_grad_vertex_pair<<<multidot_blocks(m.nV), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g, pdir,
+                                                              g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc);
     count_launch();
 }
 

@@ -1,4 +1,5 @@
 #include "linalg.h"
+#include "reduce.cuh"
 
 namespace dotgpu {
 namespace {
@@ -225,7 +226,7 @@ constexpr int MD_MAX_BLOCKS = 296;  // 2 CTAs per SM
 
 __global__ void __launch_bounds__(MD_TPB) k_dots(long long n, DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
                                                  double* __restrict__ sc) {
-    __shared__ double sh[8];
+    __shared__ double sh[8 * 12], res[12];
     __shared__ bool last;
     double acc[12];
 #pragma unroll
@@ -235,26 +236,8 @@ __global__ void __launch_bounds__(MD_TPB) k_dots(long long n, DotPairs P, double
         for (int j = 0; j < 12; ++j)
             if (j < P.n) acc[j] += P.a[j][i] * P.b[j][i];
     }
-    for (int j = 0; j < P.n; ++j) {
-        double r = cta_sum256(acc[j], sh);
-        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int j = 0; j < P.n; ++j) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += MD_TPB) v += __ldcg(partial + (size_t)j * gridDim.x + i);
-        double tot = cta_sum256(v, sh);
-        if (threadIdx.x == 0) sc[P.out[j]] = tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *counter = 0u;
+    if (!multi_reduce_256<12>(acc, P.n, sh, res, &last, partial, counter)) return;
+    if ((int)threadIdx.x < P.n) sc[P.out[threadIdx.x]] = res[threadIdx.x];
 }
 
 // compact first loop: xi_i = (s_i . q_i) / (y_i . s_i),  s_i . q_i = -(s_i . g) - sum_{j newer than i} xi_j (s_i . y_j)
@@ -350,7 +333,7 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
                                                       const double* __restrict__ go, double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                       const double* __restrict__ alpha_dev, double alpha_host, HistList H,
                                                       double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
-    __shared__ double sh[8];
+    __shared__ double shm[8 * (2 + 2 * LB_MAXH)], res[2 + 2 * LB_MAXH];
     __shared__ bool last;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
     double acc[2 + 2 * LB_MAXH];
@@ -373,34 +356,43 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
             }
     }
     const int nacc = Sn ? 2 + 2 * H.n : 2;
-    for (int j = 0; j < nacc; ++j) {
-        double r = cta_sum256(acc[j], sh);
-        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int j = 0; j < nacc; ++j) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += MD_TPB) v += __ldcg(partial + (size_t)j * gridDim.x + i);
-        double tot = cta_sum256(v, sh);
-        if (threadIdx.x == 0) {
-            if (j == 0) sc[SC_GG] = tot;
-            else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
-            else {
-                const int h = (j - 2) >> 1, sh_ = H.slot[h];
-                if ((j & 1) == 0) sc[SC_SY + 8 * sh_ + sl] = tot;  // s_h . y_new
-                else sc[SC_SY + 8 * sl + sh_] = tot;               // s_new . y_h
-            }
+    if (!multi_reduce_256<2 + 2 * LB_MAXH>(acc, nacc, shm, res, &last, partial, counter)) return;
+    if ((int)threadIdx.x < nacc) {
+        const int j = threadIdx.x;
+        const double tot = res[j];
+        if (j == 0) sc[SC_GG] = tot;
+        else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
+        else {
+            const int h = (j - 2) >> 1, sh_ = H.slot[h];
+            if ((j & 1) == 0) sc[SC_SY + 8 * sh_ + sl] = tot;  // s_h . y_new
+            else sc[SC_SY + 8 * sl + sh_] = tot;               // s_new . y_h
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *counter = 0u;
+}
+
+// p = D^-1 sum of the subdomain copies (DOTTimeStepper.cpp:434-450) and, in the same pass, the inner products of p with the
+// vectors of P (second multi-dot of the iteration): one launch instead of two.
+__global__ void __launch_bounds__(MD_TPB) k_scatter_dots(int ndof, const int* __restrict__ cptr, const int* __restrict__ cidx,
+                                                         const double* __restrict__ xs, const int* __restrict__ dup, double* __restrict__ p,
+                                                         DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
+                                                         double* __restrict__ sc) {
+    __shared__ double shm[8 * 12], res[12];
+    __shared__ bool last;
+    double acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+    for (int d = blockIdx.x * MD_TPB + threadIdx.x; d < ndof; d += gridDim.x * MD_TPB) {
+        double v = 0.0;
+        for (int k = cptr[d]; k < cptr[d + 1]; ++k) v += xs[cidx[k]];
+        const int du = dup[d / 3];
+        if (du > 1) v /= (double)du;
+        p[d] = v;
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+            if (j < P.n) acc[j] += P.a[j][d] * v;
+    }
+    if (!multi_reduce_256<12>(acc, P.n, shm, res, &last, partial, counter)) return;
+    if ((int)threadIdx.x < P.n) sc[P.out[threadIdx.x]] = res[threadIdx.x];
 }
 
 #define EW_LAUNCH(kernel, n, ...)                                              \
@@ -437,8 +429,9 @@ void launch_velocity(int nV, double* vel, const double* x, const double* xn, dou
     long long n = 3LL * nV;
     EW_LAUNCH(k_velocity, n, n, vel, x, xn, dt);
 }
-int multidot_partial_count() { return MD_MAX_BLOCKS * (2 + 2 * LB_MAXH); }
-static int md_blocks(long long n) { return (int)std::min<long long>(MD_MAX_BLOCKS, std::max<long long>(1, (n + MD_TPB * 4 - 1) / (MD_TPB * 4))); }
+int multidot_partial_count() { return MD_MAX_BLOCKS * (4 + 3 * LB_MAXH); }
+int multidot_blocks(long long n) { return (int)std::min<long long>(MD_MAX_BLOCKS, std::max<long long>(1, (n + MD_TPB - 1) / MD_TPB)); }
+static int md_blocks(long long n) { return multidot_blocks(n); }
 
 void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
     if (P.n <= 0) return;
@@ -462,6 +455,12 @@ void launch_pair_dots(long long n, const double* p, const double* g_new, const d
                       const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
                       cudaStream_t st) {
     k_pair_dots<<<md_blocks(n), MD_TPB, 0, st>>>(n, p, g_new, g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc);
+    count_launch();
+}
+
+void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, const DotPairs& P,
+                             double* partial, unsigned* counter, double* sc, cudaStream_t st) {
+    k_scatter_dots<<<md_blocks(ndof), MD_TPB, 0, st>>>(ndof, cptr, cidx, xs, dup, p, P, partial, counter, sc);
     count_launch();
 }
 

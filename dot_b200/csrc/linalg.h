@@ -71,6 +71,7 @@ enum ScalarSlot {
     SC_COUNT = 96
 };
 int multidot_partial_count();
+int multidot_blocks(long long n);  // fixed grid of the deterministic multi-reduction kernels
 // sc[P.out[j]] = a_j . b_j for all pairs in one pass (deterministic: fixed grid, block partials, last block adds them in order)
 void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st);
 // q = -g - sum_i xi_i y_i with xi from the compact first loop (needs sc[SC_SG+slot], sc[SC_SY..]); stores xi to sc[SC_XI+slot]
@@ -88,6 +89,10 @@ void launch_axpy_dev(long long n, double* out, const double* x0, const double* p
 void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
                       const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
                       cudaStream_t st);
+
+// scatter/average of the subdomain solutions fused with the inner products p . P.a[j] -> sc[P.out[j]] (P.b is ignored)
+void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, const DotPairs& P,
+                             double* partial, unsigned* counter, double* sc, cudaStream_t st);
 
 // ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
 // b[i] = q[gidx[i]]  for the concatenated permuted right-hand sides

@@ -256,12 +256,14 @@ void Stepper::refresh() {
     if (!owned.empty()) chol.factorize(a_all.p + a_off[1], st);
 }
 
-void Stepper::precondition_dev(const double* q_dev, double* p_dev) {
+bool Stepper::precondition_dev(const double* q_dev, double* p_dev, const DotPairs* fuse) {
     const int ndof = 3 * nV;
-    if (chol.n_total > 0) {
-        chol.solve(q_dev, gidx.p, xperm.p, st);  // right-hand-side gather fused into the streamed solve
-    }
+    if (chol.n_total > 0) chol.solve(q_dev, gidx.p, xperm.p, st);  // right-hand-side gather fused into the streamed solve
     if (cfg.world == 1) {
+        if (fuse) {
+            launch_scatter_avg_dots(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, *fuse, md_partial.p, counter.p, sc.p, st);
+            return true;
+        }
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, st);
     } else {
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, nullptr, p_dev, st);
@@ -269,6 +271,7 @@ void Stepper::precondition_dev(const double* q_dev, double* p_dev) {
         k_div_dup<<<ceil_div(ndof, 256), 256, 0, st>>>(ndof, dup.p, p_dev);
         count_launch();
     }
+    return false;
 }
 
 void Stepper::frame(double* x_inout, dotgpu_frame_stats* stats) {
@@ -329,13 +332,14 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     double E = h_sc[SC_E], gg = h_sc[SC_GG];
     iter_log.insert(iter_log.end(), {0.0, E, gg});
     int iters = 0;
+    bool sg_valid = false;
     std::vector<int> free_slots;
     for (int i = 0; i <= cfg.history; ++i) free_slots.push_back(i);
     do {
         // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466), compact form: the inner
         //      products against the history are taken in two multi-dot passes, the recursions run on scalars ----
         const HistList H = hist_list();
-        if (H.n > 0) {
+        if (H.n > 0 && !sg_valid) {  // normally produced by the previous iteration's fused gradient kernel
             DotPairs P;
             P.n = H.n;
             for (int i = 0; i < H.n; ++i) { P.a[i] = H.S[i]; P.b[i] = g.p; P.out[i] = SC_SG + H.slot[i]; }
@@ -349,15 +353,15 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
             pc_ev.push_back(a);
             pc_ev.push_back(b);
         }
-        DG_CUDA(cudaEventRecord(pc_ev[2 * iters], st));
-        precondition_dev(q.p, p.p);
-        DG_CUDA(cudaEventRecord(pc_ev[2 * iters + 1], st));
         {
-            DotPairs P;
+            DotPairs P;  // second multi-dot: y_i . p0 and g . p0, taken inside the scatter pass on one GPU
             P.n = H.n + 1;
             for (int i = 0; i < H.n; ++i) { P.a[i] = H.Y[i]; P.b[i] = p.p; P.out[i] = SC_YP + H.slot[i]; }
             P.a[H.n] = g.p; P.b[H.n] = p.p; P.out[H.n] = SC_P0G;
-            launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
+            DG_CUDA(cudaEventRecord(pc_ev[2 * iters], st));
+            const bool fused = precondition_dev(q.p, p.p, &P);
+            DG_CUDA(cudaEventRecord(pc_ev[2 * iters + 1], st));
+            if (!fused) launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
         launch_lbfgs_p(n, p.p, H, sc.p, st);
         // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
@@ -368,10 +372,10 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         launch_axpy_dev(n, x.p, x0.p, p.p, sc.p + SC_ALPHA, 0.0, st);
         launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
         ++evals;
-        gradient_at(x.p, g_old.p);  // gradient at the trial point (g_old is the spare buffer until the step is accepted)
+        // gradient at the trial point (g_old is the spare buffer until the step is accepted) + new pair + the next iteration's dots
         const int sl = cfg.history > 0 ? free_slots.back() : -1;  // history+1 buffers: a candidate slot is always free
-        launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, sc.p + SC_ALPHA, 0.0, H,
-                         md_partial.p, counter.p, sc.p, st);
+        launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl,
+                             sc.p + SC_ALPHA, 0.0, H, md_partial.p, counter.p, sc.p, st);
         fetch_scalars(0, SC_COUNT);
         double alpha = h_sc[SC_ALPHA], Et = h_sc[SC_E];
         if (Et > E && alpha > 0.0) {
@@ -385,14 +389,14 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                 ++evals;
                 if (!(Et > E)) break;
             }
-            gradient_at(x.p, g_old.p);
-            launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, nullptr, alpha, H, md_partial.p,
-                             counter.p, sc.p, st);
+            launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, nullptr,
+                                 alpha, H, md_partial.p, counter.p, sc.p, st);
             fetch_scalars(0, SC_COUNT);
         }
         E = Et;
         std::swap(g.p, g_old.p);
         gg = h_sc[SC_GG];
+        sg_valid = true;  // sc[SC_SG + slot] now holds s_i . g for every pair that can be in the next history
         // ---- history update (DOTTimeStepper.cpp:476-493): keep the pair iff y.s > 0, then drop the oldest beyond `history` ----
         if (sl >= 0 && h_sc[SC_YS_NEW] > 0.0) {
             free_slots.pop_back();

@@ -66,7 +66,8 @@ struct Stepper {
     DevBuf<double> h_pos;
     void set_state(const double* x, const double* velocity);
     void get_state(double* x, double* velocity, double* xTilde);
-    void precondition_dev(const double* q_dev, double* p_dev);
+    // fuse: optional inner products p . fuse->a[j] taken in the scatter pass (single-GPU only; returns false if not fused)
+    bool precondition_dev(const double* q_dev, double* p_dev, const DotPairs* fuse = nullptr);
     void refresh();  // elemental Hessians at x, matrix fill, numeric factorisation
     double energy_at(const double* x_dev);
     void gradient_at(const double* x_dev, double* g_dev);
