@@ -685,6 +685,7 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
 
     // ---- level plans (levels merged across matrices) ----
     plan.assign(nlevels, LevelPlan());
+    level_sns.clear();
     std::vector<int> tasks;
     auto push2 = [&](int s, int a) { tasks.push_back(s); tasks.push_back(a); };
     for (int lv = 0; lv < nlevels; ++lv) {
@@ -736,6 +737,27 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
                 for (int b = 0; b <= a; ++b) push2(s, (a & 0xffff) | (b << 16));
         }
         P.update_cb.cnt = ((int)tasks.size() - P.update_cb.off) / 2;
+        // solve-panel construction, scheduled behind the pivot chain: after potrf(kb) the diagonal tile kb of L_ss^-1 is its tile
+        // inverse and block row kb of L_ss^-1 (needs L rows <= kb, final after trsm(k < kb), and the rows < kb of the inverse)
+        P.sp_diag.assign(maxsteps, Span());
+        P.sp_triinv.assign(maxsteps, Span());
+        for (int kb = 0; kb < maxsteps; ++kb) {
+            P.sp_diag[kb].off = (int)tasks.size();
+            for (int s : sns)
+                if (kb * NB < sn[s].ns) push2(s, kb);
+            P.sp_diag[kb].cnt = ((int)tasks.size() - P.sp_diag[kb].off) / 2;
+            P.sp_triinv[kb].off = (int)tasks.size();
+            for (int s : sns)
+                if (kb * NB < sn[s].ns)
+                    for (int j = 0; j < kb; ++j) push2(s, j);
+            P.sp_triinv[kb].cnt = ((int)tasks.size() - P.sp_triinv[kb].off) / 2;
+        }
+        P.sp_below.off = (int)tasks.size();
+        for (int s : sns)
+            for (int a = 0; a * 64 < sn[s].m - sn[s].ns; ++a)
+                for (int b = 0; b * NB < sn[s].ns; ++b) push2(s, (a & 0xffff) | (b << 16));
+        P.sp_below.cnt = ((int)tasks.size() - P.sp_below.off) / 2;
+        level_sns.push_back(sns);
         P.fwd.off = (int)tasks.size();
         for (int s : sns)
             for (int a = 0; a * 64 < sn[s].m; ++a) push2(s, a);
@@ -744,28 +766,6 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
         for (int s : sns)
             for (int a = 0; a * 64 < sn[s].ns; ++a) push2(s, a);
         P.bwd.cnt = ((int)tasks.size() - P.bwd.off) / 2;
-    }
-    // solve-panel construction (independent of the elimination tree: batched over all supernodes)
-    {
-        int max_nblk = 0;
-        for (int s = 0; s < nsuper_total; ++s) max_nblk = std::max(max_nblk, (sn[s].ns + NB - 1) / NB);
-        sp_diag.off = (int)tasks.size();
-        for (int s = 0; s < nsuper_total; ++s)
-            for (int a = 0; a * NB < sn[s].ns; ++a) push2(s, a);
-        sp_diag.cnt = ((int)tasks.size() - sp_diag.off) / 2;
-        sp_triinv.assign(max_nblk, Span());
-        for (int i = 1; i < max_nblk; ++i) {
-            sp_triinv[i].off = (int)tasks.size();
-            for (int s = 0; s < nsuper_total; ++s)
-                if (i * NB < sn[s].ns)
-                    for (int j = 0; j < i; ++j) push2(s, j);
-            sp_triinv[i].cnt = ((int)tasks.size() - sp_triinv[i].off) / 2;
-        }
-        sp_below.off = (int)tasks.size();
-        for (int s = 0; s < nsuper_total; ++s)
-            for (int a = 0; a * 64 < sn[s].m - sn[s].ns; ++a)
-                for (int b = 0; b * NB < sn[s].ns; ++b) push2(s, (a & 0xffff) | (b << 16));
-        sp_below.cnt = ((int)tasks.size() - sp_below.off) / 2;
     }
     if (tasks.empty()) tasks.push_back(0);
 
@@ -799,8 +799,16 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     build_solve_plan(sn, st);
+    if (!st2) DG_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    if (!ev_join) DG_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     DG_CUDA(cudaStreamSynchronize(st));
     factorized = false;
+}
+
+CholBatch::~CholBatch() {
+    for (auto& e : evs) cudaEventDestroy(e);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (st2) cudaStreamDestroy(st2);
 }
 
 int64_t CholBatch::device_bytes() const {
@@ -820,6 +828,20 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
         marks.emplace_back(tag, e);
     };
     mark("start");
+    size_t ev_used = 0;
+    auto next_event = [&]() {
+        if (ev_used == evs.size()) {
+            cudaEvent_t e;
+            DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evs.push_back(e);
+        }
+        return evs[ev_used++];
+    };
+    {   // the second stream starts behind everything already queued on the caller's stream
+        cudaEvent_t e = next_event();
+        DG_CUDA(cudaEventRecord(e, st));
+        DG_CUDA(cudaStreamWaitEvent(st2, e, 0));
+    }
     static const int potrf_dbg = std::getenv("DOTGPU_POTRF_DBG") ? std::atoi(std::getenv("DOTGPU_POTRF_DBG")) : 0;  // experiments only
     DG_CUDA(cudaMemsetAsync(L.p, 0, L.bytes(), st));
     DG_CUDA(cudaMemsetAsync(CB.p, 0, CB.bytes(), st));
@@ -843,6 +865,18 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
                                                                                  d_status.p, potrf_dbg);
                 count_launch();
                 mark("potrf");
+                // second stream, one step behind the pivot chain: tiles of the solve panels that are computable now
+                cudaEvent_t e = next_event();
+                DG_CUDA(cudaEventRecord(e, st));
+                DG_CUDA(cudaStreamWaitEvent(st2, e, 0));
+                if (P.sp_diag[kb].cnt) {
+                    k_sp_diag<<<P.sp_diag[kb].cnt, 256, 0, st2>>>((const Task2*)(T + P.sp_diag[kb].off), d_sn.p, tinv.p, Sp.p);
+                    count_launch();
+                }
+                if (P.sp_triinv[kb].cnt) {
+                    k_sp_triinv<<<P.sp_triinv[kb].cnt, 128, 0, st2>>>((const Task2*)(T + P.sp_triinv[kb].off), (int)kb, d_sn.p, L.p, tinv.p, Sp.p);
+                    count_launch();
+                }
             }
             if (P.trsm[kb].cnt) {
                 k_trsm<<<P.trsm[kb].cnt, 128, 0, st>>>((const Task2*)(T + P.trsm[kb].off), (int)kb, d_sn.p, L.p, tinv.p);
@@ -855,29 +889,25 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
                 mark("update_panel");
             }
         }
+        {   // the level's panels are final: rows below of its solve panels and the packing, on the second stream
+            cudaEvent_t e = next_event();
+            DG_CUDA(cudaEventRecord(e, st));
+            DG_CUDA(cudaStreamWaitEvent(st2, e, 0));
+            if (P.sp_below.cnt) {
+                k_sp_below<<<P.sp_below.cnt, 128, 0, st2>>>((const Task3*)(T + P.sp_below.off), d_sn.p, L.p, Sp.p);
+                count_launch();
+            }
+            pack_panels(lv, st2);
+        }
         if (P.update_cb.cnt) {
             k_update_cb<<<P.update_cb.cnt, 128, 0, st>>>((const Task3*)(T + P.update_cb.off), d_sn.p, L.p, CB.p);
             count_launch();
             mark("update_cb");
         }
     }
-    // ---- solve panels ----
-    if (sp_diag.cnt) {
-        k_sp_diag<<<sp_diag.cnt, 256, 0, st>>>((const Task2*)(T + sp_diag.off), d_sn.p, tinv.p, Sp.p);
-        count_launch();
-    }
-    for (size_t i = 1; i < sp_triinv.size(); ++i)
-        if (sp_triinv[i].cnt) {
-            k_sp_triinv<<<sp_triinv[i].cnt, 128, 0, st>>>((const Task2*)(T + sp_triinv[i].off), (int)i, d_sn.p, L.p, tinv.p, Sp.p);
-            count_launch();
-        }
-    if (sp_below.cnt) {
-        k_sp_below<<<sp_below.cnt, 128, 0, st>>>((const Task3*)(T + sp_below.off), d_sn.p, L.p, Sp.p);
-        count_launch();
-    }
-    mark("solve_panels");
-    pack_panels(st);
-    mark("pack");
+    DG_CUDA(cudaEventRecord(ev_join, st2));
+    DG_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    mark("join_solve_panels");
     factorized = true;
     if (timing && !marks.empty()) {
         cudaStreamSynchronize(st);

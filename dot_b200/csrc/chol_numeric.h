@@ -62,10 +62,10 @@ struct CholBatch {
     struct LevelPlan {
         Span extend, fwd, bwd, update_cb;
         std::vector<Span> potrf, trsm, update;  // per pivot step
+        std::vector<Span> sp_diag, sp_triinv;   // per pivot step: solve-panel tiles that become computable after potrf(kb)
+        Span sp_below, pack;                    // after the level's panels are final
     };
     std::vector<LevelPlan> plan;
-    Span sp_diag, sp_below;
-    std::vector<Span> sp_triinv;
     int max_front_all = 0;
     bool factorized = false;
     // streamed solve
@@ -78,7 +78,14 @@ struct CholBatch {
     int n_solve_tasks = 0, n_pack_tasks = 0, stage_dbl = 0, vec_dbl = 0, solve_grid = 0, solve_nstage = 3, solve_dbg = 0;
     size_t solve_smem = 0;
     void build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st);
-    void pack_panels(cudaStream_t st);
+    // second stream + events: the solve panels of a supernode are built while the pivot chain of its level / the upper levels runs
+    cudaStream_t st2 = nullptr;
+    std::vector<cudaEvent_t> evs;
+    cudaEvent_t ev_join = nullptr;
+    ~CholBatch();
+    void pack_panels(int level, cudaStream_t st);
+    std::vector<std::vector<int>> level_sns;   // supernodes (batch ids) per level
+    std::vector<Span> pack_span;               // per level, into d_ptasks
 
     // ia/ja per matrix: CSR upper patterns.  Builds symbolic + device structures.
     void analyze(const std::vector<const int32_t*>& ia, const std::vector<const int32_t*>& ja, const std::vector<int>& n,

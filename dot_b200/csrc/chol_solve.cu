@@ -551,15 +551,20 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
         T.sig_total = 0;
         T.sig_next = -1;
     }
-    // pack tasks
+    // pack tasks, grouped by level (a level is packed as soon as its panels are final)
     std::vector<int> ptasks;
-    for (int g = 0; g < nsn; ++g)
-        for (int a = 0; a * 64 < sn[g].m; ++a)
-            for (int b = 0; b * 64 < sn[g].ns; ++b)
-                if (a * 64 + 63 >= b * 64) {
-                    ptasks.push_back(g);
-                    ptasks.push_back((a & 0xffff) | (b << 16));
-                }
+    pack_span.assign(nlevels, Span());
+    for (int lv = 0; lv < nlevels; ++lv) {
+        pack_span[lv].off = (int)ptasks.size();
+        for (int g : level_sns[lv])
+            for (int a = 0; a * 64 < sn[g].m; ++a)
+                for (int b = 0; b * 64 < sn[g].ns; ++b)
+                    if (a * 64 + 63 >= b * 64) {
+                        ptasks.push_back(g);
+                        ptasks.push_back((a & 0xffff) | (b << 16));
+                    }
+        pack_span[lv].cnt = ((int)ptasks.size() - pack_span[lv].off) / 2;
+    }
     n_pack_tasks = (int)ptasks.size() / 2;
     if (ptasks.empty()) ptasks.push_back(0);
     if (chunks.empty()) chunks.assign(SOLVE_GROUP_MAX, null_chunk);
@@ -584,9 +589,10 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
     solve_grid = std::min(nsm * per_sm, std::max(1, n_solve_tasks));
 }
 
-void CholBatch::pack_panels(cudaStream_t st) {
-    if (!n_pack_tasks) return;
-    k_pack_panels<<<n_pack_tasks, 256, 0, st>>>((const Task3p*)d_ptasks.p, d_ssn.p, d_sn.p, Sp.p, Pf.p, Pb.p);
+void CholBatch::pack_panels(int level, cudaStream_t st) {
+    const Span& sp = pack_span[level];
+    if (!sp.cnt) return;
+    k_pack_panels<<<sp.cnt, 256, 0, st>>>((const Task3p*)(d_ptasks.p + sp.off), d_ssn.p, d_sn.p, Sp.p, Pf.p, Pb.p);
     count_launch();
 }
 
