@@ -255,18 +255,23 @@ __global__ void __launch_bounds__(256) k_potrf(const int* __restrict__ tasks, in
     __syncthreads();
     // ... then inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1] at 32 and at 64
     if (!(dbg & 4)) {
+    // (blocks that lie entirely in the identity padding, rows >= w, are skipped: their off-diagonal inverse blocks are zero)
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int o = 32 * p;
-        smem_gemm<16, 33>(W, T + (o + 16) * 65 + o, 65, X + o * 65 + o, 65, 1.0);
+        if (o + 16 < w) {
+            smem_gemm<16, 33>(W, T + (o + 16) * 65 + o, 65, X + o * 65 + o, 65, 1.0);
+            __syncthreads();
+            smem_gemm<16, 65>(X + (o + 16) * 65 + o, X + (o + 16) * 65 + (o + 16), 65, W, 33, -1.0);
+            __syncthreads();
+        }
+    }
+    if (32 < w) {
+        smem_gemm<32, 33>(W, T + 32 * 65, 65, X, 65, 1.0);
         __syncthreads();
-        smem_gemm<16, 65>(X + (o + 16) * 65 + o, X + (o + 16) * 65 + (o + 16), 65, W, 33, -1.0);
+        smem_gemm<32, 65>(X + 32 * 65, X + 32 * 65 + 32, 65, W, 33, -1.0);
         __syncthreads();
     }
-    smem_gemm<32, 33>(W, T + 32 * 65, 65, X, 65, 1.0);
-    __syncthreads();
-    smem_gemm<32, 65>(X + 32 * 65, X + 32 * 65 + 32, 65, W, 33, -1.0);
-    __syncthreads();
     }
     double* __restrict__ tinvp = tinv + d.tinv + (long long)kb * NB * NB;
     for (int e = threadIdx.x; e < 64 * 64; e += 256) {

@@ -32,7 +32,10 @@ namespace {
 
 constexpr int SOLVE_GROUP_MAX = 4;  // chunks claimed together (they share one gather of the supernode's vector); queue slots are padded to it
 constexpr int CONSUMERS = 128;   // 4 warps: row . vector products
-constexpr int GATHERERS = 128;   // 4 warps: dependency waits + vector gathers, one supernode ahead of the consumers
+#ifndef DOTGPU_GATHERERS
+#define DOTGPU_GATHERERS 128
+#endif
+constexpr int GATHERERS = DOTGPU_GATHERERS;   // warps x 32: dependency waits + vector gathers, one supernode ahead of the consumers
 constexpr int SOLVE_THREADS = CONSUMERS + 32 + GATHERERS + 32;  // consumers, producer warp, gatherers, signaller warp
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -87,7 +90,7 @@ __device__ __forceinline__ void gatherer_sync() { asm volatile("bar.sync 2, %0;"
 // The global-memory latencies (queue, descriptors, dependency polls, gathers, fences) all sit in the helper warps and overlap the
 // consumers' work on earlier chunks.
 template <int NSTAGE>
-__global__ void __launch_bounds__(SOLVE_THREADS, 3)
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
     k_solve_stream(int ngroups, const SolveTask* __restrict__ chunks, const int* __restrict__ rows,
                    const int* __restrict__ rel, const double* __restrict__ Pf, const double* __restrict__ Pb, const double* __restrict__ b,
                    const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, unsigned* claim, int stage_dbl,
@@ -436,7 +439,9 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
         const char* v = std::getenv(name);
         return v && *v ? std::atoi(v) : dflt;
     };
-    const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", 2560);
+    // measured on B200 (profiles/r1/solve_sweep_last.json): 20 KB stages are best while the sweeps are dependency-latency
+    // bound (bar17K_like: 0.152 vs 0.161 ms), 24 KB once they are throughput bound (bar1M: 0.777 vs 0.851 ms)
+    const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", pk_total * 8 > (600LL << 20) ? 3072 : 2560);
     solve_dbg = env_int("DOTGPU_SOLVE_DBG", 0);  // experiments only: 1 skip the products, 2 skip the TMA copies, 4 skip dependency waits
     solve_nstage = std::min(4, std::max(2, env_int("DOTGPU_SOLVE_NSTAGE", 2)));
     const int max_group = std::min(SOLVE_GROUP_MAX, std::max(1, env_int("DOTGPU_SOLVE_GROUP", SOLVE_GROUP_MAX)));

@@ -7,7 +7,7 @@ out = []
 for wlname in sys.argv[1:] or ["bar17K_like", "bar1M"]:
     wl = load_workload(wlname)
     anim = D.Anim(wl["anim"], wl["V"]); fm = anim.fixed_mask()
-    for stage, nst, grp, dbg in [(2560, 2, 4, 0), (3072, 2, 4, 0), (3072, 3, 4, 0), (2560, 3, 4, 0), (2304, 4, 4, 0), (3584, 2, 4, 0), (4096, 2, 4, 0), (3072, 3, 2, 0), (3072, 3, 1, 0), (4608, 2, 4, 0)]:
+    for stage, nst, grp, dbg in [(2560, 2, 4, 0), (1792, 2, 4, 0), (1920, 2, 4, 0), (2048, 2, 4, 0), (3072, 2, 4, 0), (1536, 3, 4, 0)]:
         os.environ["DOTGPU_SOLVE_STAGE_DBL"] = str(stage); os.environ["DOTGPU_SOLVE_NSTAGE"] = str(nst); os.environ["DOTGPU_SOLVE_GROUP"] = str(grp); os.environ["DOTGPU_SOLVE_DBG"] = str(dbg)
         try:
             stp = D.Stepper(wl["V"], wl["T"], wl["epart"], fm, energy=wl["energy"], k=wl["k"], dt=DT)
