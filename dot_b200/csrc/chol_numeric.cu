@@ -70,38 +70,45 @@ __global__ void k_scatter_a(long long nnz, const long long* __restrict__ amap, c
     if (i < nnz) L[amap[i]] = a[i];
 }
 
-// ---- extend-add: parent-driven, one CTA per (parent, 64-row slab), children processed in order ----
-__global__ void __launch_bounds__(256) k_extend_add(const Task2* __restrict__ tasks, const SNDesc* __restrict__ sn,
+// ---- extend-add: parent-driven, one CTA per (parent, 64-row slab, 128-column slab of the parent front), children processed
+// in order (deterministic).  The 2-D split keeps the top levels, where a handful of parents receive large contribution blocks,
+// spread over enough CTAs. ----
+// column slabs of 128 only for fronts above `split_m` rows; the host passes INT_MAX for levels that have enough parents to fill the
+// GPU anyway (splitting then only adds overhead)
+constexpr int EA_COLS = 128, EA_SPLIT_M = 512, EA_FEW_PARENTS = 96;
+__host__ __device__ inline int ea_col_width(int m, int split_m) { return m > split_m ? EA_COLS : m; }
+__global__ void __launch_bounds__(256) k_extend_add(const Task3* __restrict__ tasks, const SNDesc* __restrict__ sn,
                                                     const int* __restrict__ rel, const int* __restrict__ child,
-                                                    double* __restrict__ L, double* __restrict__ CB) {
-    const Task2 tk = tasks[blockIdx.x];
+                                                    double* __restrict__ L, double* __restrict__ CB, int split_m) {
+    const Task3 tk = tasks[blockIdx.x];
     const SNDesc p = sn[tk.s];
     const int lo = tk.a * 64, hi = min(lo + 64, p.m);
+    const int cw = ea_col_width(p.m, split_m);
+    const int clo = tk.b * cw, chi = min(clo + cw, p.m);
     const int nbp = p.m - p.ns;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int s_rng[2];
+    __shared__ int s_rng[4];
     for (int ci = p.child_begin; ci < p.child_end; ++ci) {
         const SNDesc c = sn[child[ci]];
         const int nbc = c.m - c.ns;
         const int* __restrict__ crel = rel + c.rows + c.ns;  // [nbc], ascending
-        if (threadIdx.x == 0) {
-            int a = 0, b = nbc;  // first i with crel[i] >= lo
-            while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < lo) a = mid + 1; else b = mid; }
-            s_rng[0] = a;
-            b = nbc;             // first i with crel[i] >= hi
-            while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < hi) a = mid + 1; else b = mid; }
-            s_rng[1] = a;
+        if (threadIdx.x < 4) {  // first index with crel[i] >= {lo, hi, clo, chi}
+            const int key = threadIdx.x == 0 ? lo : (threadIdx.x == 1 ? hi : (threadIdx.x == 2 ? clo : chi));
+            int a = 0, b = nbc;
+            while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < key) a = mid + 1; else b = mid; }
+            s_rng[threadIdx.x] = a;
         }
         __syncthreads();
-        const int i0 = s_rng[0], i1 = s_rng[1];
+        const int i0 = s_rng[0], i1 = s_rng[1], j0 = s_rng[2], j1 = s_rng[3];
         const double* __restrict__ ccb = CB + c.cb;
         for (int i = i0 + warp; i < i1; i += 8) {
             const int r = crel[i];
             double* __restrict__ prow_l = L + p.panel + (long long)r * p.ns;
             double* __restrict__ prow_c = CB + p.cb + (long long)(r - p.ns) * nbp - p.ns;
             const double* __restrict__ crow = ccb + (long long)i * nbc;
+            const int jend = min(j1, i + 1);  // lower triangle of the child's contribution block
             // four independent read-modify-writes in flight per lane (targets of one child row are distinct)
-            for (int jb = lane; jb <= i; jb += 128) {
+            for (int jb = j0 + lane; jb < jend; jb += 128) {
                 double* ptr[4];
                 double v[4], o[4];
 #pragma unroll
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(256) k_extend_add(const Task2* __restrict__ ta
                     const int j = jb + 32 * q;
                     ptr[q] = nullptr;
                     v[q] = 0.0;
-                    if (j <= i) {
+                    if (j < jend) {
                         const int cc = crel[j];
                         ptr[q] = cc < p.ns ? prow_l + cc : prow_c + cc;
                         v[q] = crow[j];
@@ -703,9 +710,14 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
         }
         // extend-add
         P.extend.off = (int)tasks.size();
+        int nparents = 0;
+        for (int s : sns) nparents += sn[s].child_end > sn[s].child_begin;
+        P.extend_split_m = nparents < EA_FEW_PARENTS ? EA_SPLIT_M : 0x7fffffff;
         for (int s : sns)
             if (sn[s].child_end > sn[s].child_begin)
-                for (int a = 0; a * 64 < sn[s].m; ++a) push2(s, a);
+                for (int a = 0; a * 64 < sn[s].m; ++a)
+                    for (int b = 0; b * ea_col_width(sn[s].m, P.extend_split_m) < std::min(sn[s].m, a * 64 + 64); ++b)
+                        push2(s, (a & 0xffff) | (b << 16));  // columns <= rows
         P.extend.cnt = ((int)tasks.size() - P.extend.off) / 2;
         int maxsteps = 0;
         for (int s : sns) maxsteps = std::max(maxsteps, (sn[s].ns + NB - 1) / NB);
@@ -860,7 +872,8 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
     for (int lv = 0; lv < nlevels; ++lv) {
         const LevelPlan& P = plan[lv];
         if (P.extend.cnt) {
-            k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task2*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p);
+            k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task3*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p,
+                                                          P.extend_split_m);
             count_launch();
             mark("extend_add");
         }

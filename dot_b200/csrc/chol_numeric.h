@@ -61,6 +61,7 @@ struct CholBatch {
     struct Span { int off = 0, cnt = 0; };
     struct LevelPlan {
         Span extend, fwd, bwd, update_cb;
+        int extend_split_m = 0x7fffffff;        // extend-add: fronts above this many rows are split into column slabs
         std::vector<Span> potrf, trsm, update;  // per pivot step
         std::vector<Span> sp_diag, sp_triinv;   // per pivot step: solve-panel tiles that become computable after potrf(kb)
         Span sp_below, pack;                    // after the level's panels are final

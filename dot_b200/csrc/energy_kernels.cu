@@ -17,6 +17,7 @@ thread_local int64_t g_launch_count = 0;
 namespace {
 
 constexpr int TPB = 128;
+constexpr int ETPB = 256;  // K1: fewer, fatter CTAs -> fewer partials for the last block
 
 struct TetIn {
     Mat3 F;
@@ -70,17 +71,17 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // every block stores its partial sum, the last block to finish adds them in a fixed order:
 //   out = coef * sum(partial[0..nbT)) + sum(partial[nbT..nbT+nbV))          (deterministic, bit-reproducible)
 template <int EN>
-__global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
+__global__ void __launch_bounds__(ETPB) k_energy(int nT, int nV, int nbT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
                                                 const double* __restrict__ vol, const double* __restrict__ mu,
                                                 const double* __restrict__ lam, const double* __restrict__ x,
                                                 const double* __restrict__ xt, const double* __restrict__ mass, double coef,
                                                 double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ out,
                                                 double* __restrict__ per_elem) {
-    __shared__ double sh[TPB / 32];
+    __shared__ double sh[ETPB / 32];
     __shared__ bool last;
     double e = 0.0;
     if ((int)blockIdx.x < nbT) {  // grid-stride over the tets: a bounded number of partials keeps the final pass short
-        for (int t = blockIdx.x * TPB + threadIdx.x; t < nT; t += nbT * TPB) {
+        for (int t = blockIdx.x * ETPB + threadIdx.x; t < nT; t += nbT * ETPB) {
             TetIn in;
             load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
             const double et = energy_density<EN>(in.F, in.mu, in.lam) * in.vol;
@@ -89,13 +90,13 @@ __global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const i
         }
     } else {
         const int nbV = gridDim.x - nbT;
-        for (int v = (blockIdx.x - nbT) * TPB + threadIdx.x; v < nV; v += nbV * TPB) {
+        for (int v = (blockIdx.x - nbT) * ETPB + threadIdx.x; v < nV; v += nbV * ETPB) {
             double a = x[3 * (size_t)v] - xt[3 * (size_t)v], b = x[3 * (size_t)v + 1] - xt[3 * (size_t)v + 1],
                    c = x[3 * (size_t)v + 2] - xt[3 * (size_t)v + 2];
             e += (a * a + b * b + c * c) * mass[v] / 2.0;
         }
     }
-    double s = block_sum<TPB>(e, sh);
+    double s = block_sum<ETPB>(e, sh);
     if (!out) return;  // per-element mode
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = s;
@@ -107,12 +108,12 @@ __global__ void __launch_bounds__(TPB) k_energy(int nT, int nV, int nbT, const i
     __threadfence();
     const int nb = gridDim.x;
     double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nbT; i += TPB) a += __ldcg(partial + i);
-    for (int i = nbT + threadIdx.x; i < nb; i += TPB) b += __ldcg(partial + i);
+    for (int i = threadIdx.x; i < nbT; i += ETPB) a += __ldcg(partial + i);
+    for (int i = nbT + threadIdx.x; i < nb; i += ETPB) b += __ldcg(partial + i);
     __syncthreads();
-    double sa = block_sum<TPB>(a, sh);
+    double sa = block_sum<ETPB>(a, sh);
     __syncthreads();
-    double sb = block_sum<TPB>(b, sh);
+    double sb = block_sum<ETPB>(b, sh);
     if (threadIdx.x == 0) {
         out[0] = coef * sa + sb;
         *counter = 0u;
@@ -404,7 +405,7 @@ void DeviceMesh::init(int energy_type, int nV_, int nT_, const int32_t* tets_h, 
         vp_idx.upload(vidx, st);
         gpart.alloc(3 * (size_t)std::max(npart, 1));
     }
-    n_partial = ceil_div(nT, TPB) + ceil_div(nV, TPB);
+    n_partial = 148 * 8 + 8;
     partial.alloc(n_partial);
     counter.alloc(1);
     counter.zero(st);
@@ -426,15 +427,15 @@ void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
     } while (0)
 
 void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st) {
-    // at most 12 tet CTAs + 2 inertia CTAs per SM (148 SMs): <= 2072 partials for the last block
-    const int nbT = std::min(ceil_div(m.nT, TPB), 148 * 12), nbV = xTilde ? std::min(ceil_div(m.nV, TPB), 148 * 2) : 0;
-    DISPATCH_EN(m, k_energy, nbT + nbV, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, xTilde,
+    // at most 6 tet CTAs + 1 inertia CTA of 256 threads per SM (148 SMs): <= 1036 partials for the last block
+    const int nbT = std::min(ceil_div(m.nT, ETPB), 148 * 6), nbV = xTilde ? std::min(ceil_div(m.nV, ETPB), 148) : 0;
+    DISPATCH_EN(m, k_energy, nbT + nbV, ETPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, xTilde,
                 m.mass.p, coef, m.partial.p, m.counter.p, E_out, (double*)nullptr);
 }
 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st) {
-    const int nbT = std::min(ceil_div(m.nT, TPB), 148 * 12);
-    DISPATCH_EN(m, k_energy, nbT, TPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
+    const int nbT = std::min(ceil_div(m.nT, ETPB), 148 * 6);
+    DISPATCH_EN(m, k_energy, nbT, ETPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
                 (const double*)nullptr, (const double*)nullptr, 1.0, (double*)nullptr, (unsigned*)nullptr, (double*)nullptr, out);
 }
 
