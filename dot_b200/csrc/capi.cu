@@ -1,4 +1,5 @@
 // extern "C" surface of libdotgpu (include/dotgpu.h).  No exceptions cross this boundary.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -292,7 +293,14 @@ int dotgpu_solver_solve(dotgpu_solver* s, const double* rhs, double* x) {
     DG_CUDA(cudaSetDevice(s->device));
     const int n = s->n;
     s->tmp.upload(rhs, n, s->st);
-    s->chol.solve(s->tmp.p, s->d_perm.p, s->x.p, s->st);
+    static const bool by_levels = std::getenv("DOTGPU_SOLVE_LEVELS") != nullptr;  // cross-check path: one launch per level and direction
+    if (by_levels) {
+        k_permute_in<<<ceil_div(n, 256), 256, 0, s->st>>>(n, s->d_perm.p, s->tmp.p, s->b.p);
+        s->chol.solve_levels(s->b.p, s->x.p, s->st);
+        count_launch(1);
+    } else {
+        s->chol.solve(s->tmp.p, s->d_perm.p, s->x.p, s->st);
+    }
     k_permute_out<<<ceil_div(n, 256), 256, 0, s->st>>>(n, s->d_perm.p, s->x.p, s->tmp.p);
     count_launch(1);
     s->tmp.download(x, n, s->st);

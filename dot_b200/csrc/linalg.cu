@@ -119,40 +119,12 @@ __global__ void __launch_bounds__(DOT_TPB) k_dot(long long n, const double* __re
     }
 }
 
-__global__ void k_axpy_sc(long long n, double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ sc, int num, int den,
-                          double sign) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double c = sign * sc[num] / (den >= 0 ? sc[den] : 1.0);
-    y[i] += c * x[i];
-}
 
-__global__ void k_lbfgs_first(long long n, double* __restrict__ q, const double* __restrict__ y, double* __restrict__ sc, int dot, int ys,
-                              int ksi) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const double k = sc[dot] / sc[ys];
-    if (i < n) q[i] -= k * y[i];
-    if (i == 0) sc[ksi] = k;  // read by the second loop (launched later on the same stream)
-}
 
-__global__ void k_lbfgs_second(long long n, double* __restrict__ p, const double* __restrict__ s, const double* __restrict__ sc, int dot,
-                               int ys, int ksi) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    p[i] += s[i] * (sc[ksi] - sc[dot] / sc[ys]);
-}
 
-__global__ void k_scale_copy(long long n, double* __restrict__ out, const double* __restrict__ in, double alpha) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = alpha * in[i];
-}
 __global__ void k_axpy(long long n, double* __restrict__ out, const double* __restrict__ x0, const double* __restrict__ p, double alpha) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = x0[i] + alpha * p[i];
-}
-__global__ void k_sub(long long n, double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = a[i] - b[i];
 }
 __global__ void k_warm_start(int nV, double* __restrict__ x, const double* __restrict__ vel, const unsigned char* __restrict__ fixed, double dt,
                              double gx, double gy, double gz) {
@@ -174,10 +146,6 @@ __global__ void k_xtilde(int nV, double* __restrict__ xt, const double* __restri
 __global__ void k_velocity(long long n, double* __restrict__ vel, const double* __restrict__ x, const double* __restrict__ xn, double dt) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vel[i] = (x[i] - xn[i]) / dt;
-}
-__global__ void k_gather(long long n, const int* __restrict__ gidx, const double* __restrict__ q, double* __restrict__ b) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) b[i] = q[gidx[i]];
 }
 __global__ void k_scatter_avg(int ndof, const int* __restrict__ cptr, const int* __restrict__ cidx, const double* __restrict__ xs,
                               const int* __restrict__ dup, double* __restrict__ p) {
@@ -403,20 +371,9 @@ __global__ void __launch_bounds__(MD_TPB) k_scatter_dots(int ndof, const int* __
         }                                                                      \
     } while (0)
 
-void launch_axpy_sc(long long n, double* y, const double* x, const double* sc, int num, int den, double sign, cudaStream_t st) {
-    EW_LAUNCH(k_axpy_sc, n, n, y, x, sc, num, den, sign);
-}
-void launch_lbfgs_first(long long n, double* q, const double* y, double* sc, int dot, int ys, int ksi, cudaStream_t st) {
-    EW_LAUNCH(k_lbfgs_first, n, n, q, y, sc, dot, ys, ksi);
-}
-void launch_lbfgs_second(long long n, double* p, const double* s, const double* sc, int dot, int ys, int ksi, cudaStream_t st) {
-    EW_LAUNCH(k_lbfgs_second, n, n, p, s, sc, dot, ys, ksi);
-}
-void launch_scale_copy(long long n, double* out, const double* in, double alpha, cudaStream_t st) { EW_LAUNCH(k_scale_copy, n, n, out, in, alpha); }
 void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st) {
     EW_LAUNCH(k_axpy, n, n, out, x0, p, alpha);
 }
-void launch_sub(long long n, double* out, const double* a, const double* b, cudaStream_t st) { EW_LAUNCH(k_sub, n, n, out, a, b); }
 void launch_warm_start(int nV, double* x, const double* vel, const unsigned char* fixed, double dt, double gx, double gy, double gz,
                        cudaStream_t st) {
     EW_LAUNCH(k_warm_start, nV, nV, x, vel, fixed, dt, gx, gy, gz);
@@ -464,7 +421,6 @@ void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const d
     count_launch();
 }
 
-void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st) { EW_LAUNCH(k_gather, n, n, gidx, q, b); }
 void launch_scatter_avg(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, cudaStream_t st) {
     EW_LAUNCH(k_scatter_avg, ndof, ndof, cptr, cidx, xs, dup, p);
 }

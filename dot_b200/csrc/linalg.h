@@ -29,16 +29,7 @@ void launch_spmv_sym(int n, const int* ia, const int* ja, const double* a, const
 int dot_partial_count(long long n);
 // sc[k] = a.b    (partial must hold dot_partial_count(n) doubles, counter one zeroed unsigned)
 void launch_dot(long long n, const double* a, const double* b, double* partial, unsigned* counter, double* sc_out, cudaStream_t st);
-// y += (sc[num] / sc[den]) * x * sign   (den < 0 => divisor 1)
-void launch_axpy_sc(long long n, double* y, const double* x, const double* sc, int num, int den, double sign, cudaStream_t st);
-// two-loop helpers (DOTTimeStepper.cpp:389-398, 459-466):
-//   first loop : ksi = (s.q)/ys ; q -= ksi*y      -> dot into sc[DOT], then this with coefficient sc[dot]/sc[ys], result stored to sc[ksi]
-void launch_lbfgs_first(long long n, double* q, const double* y, double* sc, int dot, int ys, int ksi, cudaStream_t st);
-//   second loop: p += s * (ksi - (y.p)/ys)
-void launch_lbfgs_second(long long n, double* p, const double* s, const double* sc, int dot, int ys, int ksi, cudaStream_t st);
-void launch_scale_copy(long long n, double* out, const double* in, double alpha, cudaStream_t st);            // out = alpha*in
 void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st);  // out = x0 + alpha*p
-void launch_sub(long long n, double* out, const double* a, const double* b, cudaStream_t st);                 // out = a - b
 // initX + xTilde (Optimizer.cpp:472-493, 585-610): x += (dt v + dt^2 g) on free verts
 void launch_warm_start(int nV, double* x, const double* vel, const unsigned char* fixed, double dt, double gx, double gy, double gz,
                        cudaStream_t st);
@@ -95,8 +86,6 @@ void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const d
                              double* partial, unsigned* counter, double* sc, cudaStream_t st);
 
 // ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
-// b[i] = q[gidx[i]]  for the concatenated permuted right-hand sides
-void launch_gather(long long n, const int* gidx, const double* q, double* b, cudaStream_t st);
 // p[d] = (sum over the subdomain copies of dof d, in subdomain order) / dup
 void launch_scatter_avg(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, cudaStream_t st);
 

@@ -23,10 +23,6 @@ __global__ void k_set_rows(int count, const int* __restrict__ idx, const double*
     x[3 * (size_t)v + 1] = pos[3 * i + 1];
     x[3 * (size_t)v + 2] = pos[3 * i + 2];
 }
-__global__ void k_neg(long long n, double* __restrict__ out, const double* __restrict__ in) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = -in[i];
-}
 }  // namespace
 
 Stepper::~Stepper() {
@@ -205,7 +201,6 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
         b->alloc(n3);
         b->zero(st);
     }
-    bperm.alloc(std::max<int64_t>(chol.n_total, 1));
     xperm.alloc(std::max<int64_t>(chol.n_total, 1));
     qf_partial.alloc(ceil_div((long long)n3, 256) + 1);
     dot_partial.alloc(dot_partial_count((long long)n3));

@@ -39,7 +39,7 @@ struct Stepper {
     DeviceFill fill;
     CholBatch chol;
     DevBuf<int> gidx, cptr, cidx, dup;
-    DevBuf<double> x, x0, xn, xt, vel, g, g_old, q, p, bperm, xperm, qf_partial, dot_partial, md_partial;
+    DevBuf<double> x, x0, xn, xt, vel, g, g_old, q, p, xperm, qf_partial, dot_partial, md_partial;
     HistList hist_list() const;
     std::vector<DevBuf<double>> S, Y;
     std::deque<int> hist;            // slots, oldest first

@@ -361,3 +361,57 @@ def test_dropin_unmodified_reference_steppers_over_libdotgpu(tmp_path, energy, k
     # solvers only (reference CPU energy + libdotgpu factor/solve): isolates the LinSysSolver boundary
     st_s, x_s = _run_ref_binary(gpu, str(tmp_path), script, frames, ["--tol", str(tol), "--cpu-energy"])
     assert np.abs(x_s - x_c).max() <= 1e-6 * bbox
+
+
+def test_streamed_solve_matches_level_by_level_and_is_bit_reproducible(tmp_path):
+    """K5: the persistent TMA-streamed dataflow solve against the in-library level-by-level implementation (one launch per
+    level and direction, DOTGPU_SOLVE_LEVELS=1 in a fresh process) on a C2-size subdomain matrix: same answer to 1e-13
+    (different summation order in the backward sweep only), and bit-identical from run to run (fixed summation orders)."""
+    import os
+    import subprocess
+    import sys
+    V, T = meshgen.preset("bar17K_like")
+    V = meshgen.normalise_like_loader(V)
+    ep = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels_bar17K_like_k8.npz"))["epart"].astype(np.int32)
+    a = D.Anim("twist", V)
+    stp = D.Stepper(V, T, ep, a.fixed_mask(), energy="SNH", k=8)
+    ia, ja = stp.dd().pattern(5)
+    vals = stp.matrix(5)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(ia.shape[0] - 1)
+    s = D.Solver(ia, ja)
+    s.set_values(vals)
+    s.factorize()
+    x1, x2 = s.solve(b), s.solve(b)
+    assert np.array_equal(x1, x2)
+    np.savez(tmp_path / "sys.npz", ia=ia, ja=ja, a=vals, b=b)
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); import dot_b200 as D; z = np.load(%r); s = D.Solver(z['ia'], z['ja']); "
+            "s.set_values(z['a']); s.factorize(); np.save(%r, s.solve(z['b']))" %
+            (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "sys.npz"), str(tmp_path / "x_levels.npy")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DOTGPU_SOLVE_LEVELS="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    xl = np.load(tmp_path / "x_levels.npy")
+    assert rel(x1, xl) < 1e-13
+    A = O.csr_upper_to_full(ia, ja, vals)
+    assert np.linalg.norm(A @ x1 - b) <= 1e-12 * (np.linalg.norm(b) + abs(A).sum(axis=1).max() * np.linalg.norm(x1))
+
+
+def test_frames_are_bit_reproducible():
+    """Every reduction on the path has a fixed order (no floating-point atomics): two steppers fed the same input produce
+    bit-identical positions and iteration logs."""
+    V, T = meshgen.preset("bar2K")
+    V = meshgen.normalise_like_loader(V)
+    ep = np.minimum((V[T].mean(axis=1)[:, 0] * 5).astype(np.int32), 4)
+    outs = []
+    for rep in range(2):
+        a = D.Anim("twist", V)
+        stp = D.Stepper(V, T, ep, a.fixed_mask(), energy="FCR", k=5)
+        x = V.copy()
+        logs = []
+        for f in range(3):
+            a.step(x, 0.025)
+            stp.frame(x)
+            logs.append(stp.iter_log())
+        outs.append((x.copy(), np.concatenate(logs)))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
