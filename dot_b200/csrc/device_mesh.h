@@ -6,7 +6,8 @@
 //   lv_ptr/g_cptr/g_cidx/vp_*    K2 tables: CTA-local vertex lists and per-vertex partial lists (ascending tet order,
 //                                the order of Mesh.cpp:606-611 / Energy.cpp:543-563 up to the association into CTA partials)
 //   gpart    double[3][#(CTA,vertex)]  per-CTA vertex partial gradients, scratch
-//   He       double[nT][16][9]   elemental Hessians as 4x4 blocks of 3x3 (72 contiguous bytes per block)
+//   He       double[nT][10][9]   elemental Hessians: the 10 unique 3x3 blocks (k <= l) of the symmetric 4x4 block matrix,
+//                                72 contiguous bytes per block, 720 B per tet
 #pragma once
 #include "common.h"
 
@@ -23,7 +24,7 @@ struct DeviceMesh {
     DevBuf<int> lv_ptr, vp_ptr, vp_idx;
     DevBuf<unsigned short> g_cptr, g_cidx;
     DevBuf<double> gpart;   // 3 doubles per (CTA, local vertex)
-    DevBuf<double> He;      // 144*nT, allocated on first use
+    DevBuf<double> He;      // 90*nT, allocated on first use
     DevBuf<double> partial; // block partial sums for reductions
     int n_partial = 0;
     DevBuf<unsigned> counter;  // last-block detection of the fused energy reduction (self-resetting)
@@ -44,7 +45,7 @@ void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, 
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
                           const HistList& H, double* partial, unsigned* counter, double* sc, cudaStream_t st);
 void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st);
-// fills m.He ([nT][16][9])
+// fills m.He ([nT][10][9])
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st);
 // converts m.He to the reference's row-major 12x12 layout
 void launch_he_to_dense(DeviceMesh& m, double* out144, cudaStream_t st);

@@ -287,61 +287,70 @@ __global__ void __launch_bounds__(TPB) k_svd(int nT, const int4* __restrict__ te
     if (So) for (int i = 0; i < 3; ++i) So[(size_t)3 * t + i] = S[i];
 }
 
+// K3: elemental PD-projected Hessians.  Only the 10 unique 3x3 blocks (k <= l) of the symmetric 12x12 matrix are stored
+// (He[nT][10][9], 720 B/tet instead of 1152): block (l,k) is the transpose of (k,l).  Every thread stages its 90 values in
+// shared memory and the CTA then writes its tets' contiguous 128 x 720 B region with fully coalesced stores (the direct
+// per-thread stores had a 1152-byte stride between lanes and ran at ~19 % of the HBM roofline).
+constexpr int HE_BLOCKS = 10, HE_DBL = 90, HE_LD = 91;  // 91: odd stride -> conflict-free staging
+__host__ __device__ inline int he_block(int k, int l) { return k * 4 - k * (k - 1) / 2 + (l - k); }  // k <= l
+
 template <int EN>
 __global__ void __launch_bounds__(TPB) k_hessian(int nT, const int4* __restrict__ tets, const double* __restrict__ DmInv,
                                                  const double* __restrict__ vol, const double* __restrict__ mu,
                                                  const double* __restrict__ lam, const double* __restrict__ x, double coef,
                                                  int project, double* __restrict__ He) {
-    int t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= nT) return;
-    TetIn in;
-    load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
-    Mat3 U, V;
-    double S[3];
-    svd3(in.F, U, S, V);
-    HessCoef hc;
-    hess_coef<EN>(S, in.mu, in.lam, coef * in.vol, project != 0, hc);
-    // beta[k][b] = v_b . w_k,  w_k = row k-1 of Dm^-1 (k=1..3), w_0 = -(sum of rows)
-    double beta[4][3];
+    extern __shared__ double stage[];  // [TPB][HE_LD]
+    const int t0 = blockIdx.x * TPB;
+    const int t = t0 + threadIdx.x;
+    if (t < nT) {
+        TetIn in;
+        load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
+        Mat3 U, V;
+        double S[3];
+        svd3(in.F, U, S, V);
+        HessCoef hc;
+        hess_coef<EN>(S, in.mu, in.lam, coef * in.vol, project != 0, hc);
+        // beta[k][b] = v_b . w_k,  w_k = row k-1 of Dm^-1 (k=1..3), w_0 = -(sum of rows)
+        double beta[4][3];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < 3; ++b) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            beta[k + 1][b] = in.B[3 * k] * V(0, b) + in.B[3 * k + 1] * V(1, b) + in.B[3 * k + 2] * V(2, b);
-        beta[0][b] = -(beta[1][b] + beta[2][b] + beta[3][b]);
-    }
-    double* out = He + (size_t)144 * t;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int l = k; l < 4; ++l) {
-            double blk[9];
-            hess_block(hc, U, beta[k], beta[l], blk);
-            if (k == l) {  // symmetrise the diagonal block exactly (the reference mirrors the upper part, Energy.cpp:1263-1265)
-                blk[3] = blk[1]; blk[6] = blk[2]; blk[7] = blk[5];
-            }
-            double2* o2;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) out[(4 * k + l) * 9 + i] = blk[i];
-            if (l != k) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) out[(4 * l + k) * 9 + 3 * r + i] = blk[3 * i + r];
-            }
-            (void)o2;
+            for (int k = 0; k < 3; ++k)
+                beta[k + 1][b] = in.B[3 * k] * V(0, b) + in.B[3 * k + 1] * V(1, b) + in.B[3 * k + 2] * V(2, b);
+            beta[0][b] = -(beta[1][b] + beta[2][b] + beta[3][b]);
         }
+        double* out = stage + threadIdx.x * HE_LD;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int l = k; l < 4; ++l) {
+                double blk[9];
+                hess_block(hc, U, beta[k], beta[l], blk);
+                if (k == l) {  // symmetrise the diagonal block exactly (the reference mirrors the upper part, Energy.cpp:1263-1265)
+                    blk[3] = blk[1]; blk[6] = blk[2]; blk[7] = blk[5];
+                }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) out[he_block(k, l) * 9 + i] = blk[i];
+            }
+        }
+    }
+    __syncthreads();
+    const int ntet = min(TPB, nT - t0);
+    double* __restrict__ dst = He + (size_t)HE_DBL * t0;
+    for (int e = threadIdx.x; e < ntet * HE_DBL; e += TPB) {
+        const int tt = e / HE_DBL, j = e - tt * HE_DBL;
+        dst[e] = stage[tt * HE_LD + j];
     }
 }
 
-// [nT][16][9] block layout -> row-major 12x12
+// [nT][10][9] unique blocks -> row-major 12x12 (the reference's elemHessian layout)
 __global__ void k_he_to_dense(int nT, const double* __restrict__ He, double* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nT * 144) return;
     int t = (int)(i / 144), e = (int)(i % 144);
     int row = e / 12, col = e % 12;
     int k = row / 3, ii = row % 3, l = col / 3, r = col % 3;
-    out[i] = He[(size_t)144 * t + (4 * k + l) * 9 + 3 * ii + r];
+    out[i] = k <= l ? He[(size_t)HE_DBL * t + he_block(k, l) * 9 + 3 * ii + r] : He[(size_t)HE_DBL * t + he_block(l, k) * 9 + 3 * r + ii];
 }
 
 }  // namespace
@@ -417,6 +426,15 @@ void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
     DG_CUDA(cudaStreamSynchronize(st));
 }
 
+#define DISPATCH_EN_SMEM(m, KERNEL, grid, block, smem, st, ...)                 \
+    do {                                                                       \
+        if ((m).energy == DOTGPU_ENERGY_FCR)                                   \
+            KERNEL<DG_FCR><<<grid, block, smem, st>>>(__VA_ARGS__);            \
+        else                                                                   \
+            KERNEL<DG_SNH><<<grid, block, smem, st>>>(__VA_ARGS__);            \
+        count_launch();                                                        \
+    } while (0)
+
 #define DISPATCH_EN(m, KERNEL, grid, block, st, ...)                           \
     do {                                                                       \
         if ((m).energy == DOTGPU_ENERGY_FCR)                                   \
@@ -464,9 +482,15 @@ void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S,
 }
 
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st) {
-    if (m.He.n < (size_t)144 * m.nT) m.He.alloc((size_t)144 * m.nT);
+    if (m.He.n < (size_t)HE_DBL * m.nT) m.He.alloc((size_t)HE_DBL * m.nT);
     int nb = ceil_div(m.nT, TPB);
-    DISPATCH_EN(m, k_hessian, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef,
+    static bool attr_set = false;
+    if (!attr_set) {
+        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_FCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
+        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_SNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
+        attr_set = true;
+    }
+    DISPATCH_EN_SMEM(m, k_hessian, nb, TPB, TPB * HE_LD * sizeof(double), st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef,
                 project ? 1 : 0, m.He.p);
 }
 

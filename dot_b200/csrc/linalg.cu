@@ -30,9 +30,19 @@ __global__ void __launch_bounds__(128) k_fill(long long nblk, const long long* _
     for (long long e = ptr[b]; e < ptr[b + 1]; ++e) {
         int code = src[e];
         if (code >= 0) {
-            const double* __restrict__ h = He + (long long)code * 9;
+            // code = 16*tet + 4*a + b; only blocks a <= b are stored ([nT][10][9]), (a,b) with a > b is the transpose of (b,a)
+            const int tet = code >> 4, ba = (code >> 2) & 3, bb = code & 3;
+            const int lo = min(ba, bb), hi = max(ba, bb);
+            const double* __restrict__ h = He + (long long)tet * 90 + (lo * 4 - lo * (lo - 1) / 2 + (hi - lo)) * 9;
+            if (ba <= bb) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) acc[i] += h[i];
+                for (int i = 0; i < 9; ++i) acc[i] += h[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) acc[3 * i + r] += h[3 * r + i];
+            }
         } else {
             double c = consts[-code - 1];
             acc[0] += c; acc[4] += c; acc[8] += c;
