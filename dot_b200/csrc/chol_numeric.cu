@@ -815,6 +815,10 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
     // (a smaller batch analysed later must not lower it under a larger one; occupancy follows the launch-time size)
     DG_CUDA(cudaFuncSetAttribute(k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaFuncSetAttribute(k_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (graph_exec) {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+    }
     build_solve_plan(sn, st);
     if (!st2) DG_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
     if (!ev_join) DG_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -823,6 +827,7 @@ void CholBatch::analyze(const std::vector<const int32_t*>& ia, const std::vector
 }
 
 CholBatch::~CholBatch() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (auto& e : evs) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (st2) cudaStreamDestroy(st2);
@@ -833,7 +838,7 @@ int64_t CholBatch::device_bytes() const {
                      d_amap.bytes() + d_ea_ptr.bytes() + d_ea_src.bytes() + d_tasks.bytes() + d_sn.bytes());
 }
 
-void CholBatch::factorize(const double* a_all, cudaStream_t st) {
+void CholBatch::enqueue_factorize(const double* a_all, cudaStream_t st) {
     // DOTGPU_FACTOR_TIMING=1: per-phase device times of this factorisation (CUDA events on the stream), printed to stderr
     static const bool timing = std::getenv("DOTGPU_FACTOR_TIMING") != nullptr;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
@@ -945,6 +950,45 @@ void CholBatch::factorize(const double* a_all, cudaStream_t st) {
         std::fprintf(stderr, "\n");
         for (auto& m : marks) cudaEventDestroy(m.second);
     }
+}
+
+// The launch sequence of a numeric factorisation is static (it depends on the symbolic analysis only), so it is captured into
+// a CUDA graph once - both streams, ~170 kernel nodes on bar17K_like - and replayed every frame: the dependent launches of
+// the pivot chain then follow each other without the stream-launch gaps.  DOTGPU_NO_GRAPH=1 or DOTGPU_FACTOR_TIMING=1 use
+// plain stream launches.
+void CholBatch::factorize(const double* a_all, cudaStream_t st) {
+    static const bool no_graph = std::getenv("DOTGPU_NO_GRAPH") != nullptr || std::getenv("DOTGPU_FACTOR_TIMING") != nullptr;
+    if (no_graph) {
+        enqueue_factorize(a_all, st);
+        return;
+    }
+    if (!graph_exec || graph_a != a_all || graph_st != st) {
+        if (graph_exec) {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+        }
+        const int64_t before = g_launch_count;
+        cudaGraph_t graph = nullptr;
+        DG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_factorize(a_all, st);
+        } catch (...) {
+            cudaStreamEndCapture(st, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        DG_CUDA(cudaStreamEndCapture(st, &graph));
+        graph_launches = g_launch_count - before;
+        g_launch_count = before;
+        const cudaError_t ie = cudaGraphInstantiate(&graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        DG_CUDA(ie);
+        graph_a = a_all;
+        graph_st = st;
+    }
+    DG_CUDA(cudaGraphLaunch(graph_exec, st));
+    count_launch((int)graph_launches);
+    factorized = true;
 }
 
 void CholBatch::check_status(cudaStream_t st) {

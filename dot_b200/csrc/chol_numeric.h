@@ -93,6 +93,11 @@ struct CholBatch {
                  int leaf_nodes, cudaStream_t st);
     // a_all: device pointer to the concatenated CSR values (pattern order) of all matrices of the batch
     void factorize(const double* a_all, cudaStream_t st);
+    void enqueue_factorize(const double* a_all, cudaStream_t st);  // the plain launch sequence (captured into a graph by factorize)
+    cudaGraphExec_t graph_exec = nullptr;
+    const double* graph_a = nullptr;
+    cudaStream_t graph_st = nullptr;
+    int64_t graph_launches = 0;
     // throws Error(DOTGPU_ERR_NOT_SPD) if the last factorize met a non-positive pivot (syncs the stream)
     void check_status(cudaStream_t st);
     // x_perm: device vector of n_total doubles in the PERMUTED order of each matrix (x_perm[col_off[m] + i] = x_m[perm_m[i]]).
