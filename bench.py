@@ -37,6 +37,8 @@ WORKLOADS = {
     "bar5K_like": ("bar5K_like", "FCR", 6, "twist"),
     "bar136K_like": ("bar136K_like", "FCR", 64, "twist"),
     "bar1M": ("bar1M", "SNH", 128, "twist"),
+    # BASELINE config C1 ("1 subdomain" = the reference's `timeStepper Newton`): Projected Newton, FCR
+    "bar5K_like_PN": ("bar5K_like", "FCR", 1, "twist"),
 }
 DT = 0.025
 
@@ -46,8 +48,12 @@ def load_workload(name):
     preset, energy, k, anim = WORKLOADS[name]
     V, T = meshgen.preset(preset)
     Vn = meshgen.normalise_like_loader(V)
-    ep = np.load(os.path.join(ROOT, "tests", "golden", "labels_%s_k%d.npz" % (preset, k)))["epart"].astype(np.int32)
-    return dict(name=name, preset=preset, energy=energy, k=k, anim=anim, V_raw=V, V=Vn, T=T, epart=ep)
+    newton = name.endswith("_PN")
+    if newton:
+        ep = np.zeros(T.shape[0], dtype=np.int32)
+    else:
+        ep = np.load(os.path.join(ROOT, "tests", "golden", "labels_%s_k%d.npz" % (preset, k)))["epart"].astype(np.int32)
+    return dict(name=name, preset=preset, energy=energy, k=k, anim=anim, V_raw=V, V=Vn, T=T, epart=ep, newton=newton)
 
 
 def peaks():
@@ -96,7 +102,7 @@ def run_reference(wl, steps, warmup, threads=None):
     msh = os.path.join(tmp, "mesh.msh")
     meshgen.write_msh(msh, wl["V_raw"], wl["T"])
     script = os.path.join(tmp, "script.txt")
-    meshgen.write_script(script, msh, energy=wl["energy"], parts=wl["k"], anim=wl["anim"], dt=DT)
+    meshgen.write_script(script, msh, energy=wl["energy"], parts=wl["k"], anim=wl["anim"], dt=DT, stepper="Newton" if wl["newton"] else "DOT")
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
     blas = os.path.join(ROOT, "oracle", "_ref", "blasdir.txt")
     if os.path.exists(blas):
@@ -196,7 +202,7 @@ def main():
 
     def make():
         return D.Stepper(wl["V"], wl["T"], wl["epart"], fm, energy=wl["energy"], k=wl["k"], dt=DT, device=local_rank, rank=rank, world=world,
-                         nccl_id=fresh_nccl_id())
+                         nccl_id=fresh_nccl_id(), newton=wl["newton"])
 
     # ---------------- value: resident positions ----------------
     t_setup = time.time()

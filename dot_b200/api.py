@@ -298,10 +298,11 @@ class Anim:
 
 
 class Stepper:
-    """Device-resident DOT time stepper (DOTTimeStepper)."""
+    """Device-resident time stepper: DOT (DOTTimeStepper) or, with newton=True and a single subdomain, Projected Newton
+    (Optimizer::solve_oneStep, the reference's `timeStepper Newton`)."""
 
     def __init__(self, V_rest, tets, epart, fixed_mask, energy="SNH", k=None, dt=0.025, device=0, rel_tol=1e-5, YM=1e5, PR=0.4,
-                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000):
+                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000, newton=False):
         V = _f64(V_rest)
         T = _i32(tets)
         ep = _i32(epart)
@@ -317,6 +318,8 @@ class Stepper:
         cfg.YM, cfg.PR, cfg.rho = YM, PR, rho
         cfg.max_iters = max_iters
         cfg.rank, cfg.world = rank, world
+        if newton:
+            cfg.flags |= 2  # DOTGPU_FLAG_NEWTON
         self._id = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         cfg.nccl_unique_id = C.cast(self._id, C.c_void_p) if self._id is not None else None
         self.cfg = cfg

@@ -439,9 +439,14 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
         const char* v = std::getenv(name);
         return v && *v ? std::atoi(v) : dflt;
     };
-    // measured on B200 (profiles/r1/solve_sweep_last.json): 20 KB stages are best while the sweeps are dependency-latency
-    // bound (bar17K_like: 0.152 vs 0.161 ms), 24 KB once they are throughput bound (bar1M: 0.777 vs 0.851 ms)
-    const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", pk_total * 8 > (600LL << 20) ? 3072 : 2560);
+    // Stage size: the largest (multiple of 256 doubles, <= 3072) that still lets THREE CTAs share an SM's shared memory
+    // next to the two vector buffers - measured on B200 (profiles/r1/solve_sweep_last.json): the third CTA is worth more than
+    // bigger stages (bar136K_like: 0.58 ms with 3 CTAs x 20 KB stages vs 0.73 ms with 2 CTAs x 24 KB), and among 3-CTA
+    // configurations bigger stages win (bar1M: 0.78 ms at 24 KB vs 0.85 ms at 20 KB).
+    const int vec_bytes = 24 * (((max_front_all + 8 + 15) / 16) * 16);
+    int auto_stage = ((73 * 1024 - vec_bytes) / 16) / 256 * 256;
+    auto_stage = std::max(1536, std::min(3072, auto_stage));
+    const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", auto_stage);
     solve_dbg = env_int("DOTGPU_SOLVE_DBG", 0);  // experiments only: 1 skip the products, 2 skip the TMA copies, 4 skip dependency waits
     solve_nstage = std::min(4, std::max(2, env_int("DOTGPU_SOLVE_NSTAGE", 2)));
     const int max_group = std::min(SOLVE_GROUP_MAX, std::max(1, env_int("DOTGPU_SOLVE_GROUP", SOLVE_GROUP_MAX)));

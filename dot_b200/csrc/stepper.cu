@@ -90,6 +90,11 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= 8, "bad subdomain count / history size");
     DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
     DG_REQUIRE(cfg.dt > 0, "dt must be positive");
+    newton = (cfg.flags & DOTGPU_FLAG_NEWTON) != 0;
+    if (newton) {
+        DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
+        cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DOTGPU_ERR_NO_DEVICE, "no CUDA device");
     DG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device index out of range");
@@ -333,6 +338,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     do {
         // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466), compact form: the inner
         //      products against the history are taken in two multi-dot passes, the recursions run on scalars ----
+        if (newton) refresh();  // Optimizer::solve_oneStep: computePrecondMtr + factorize at the current iterate (Optimizer.cpp:703-730)
         const HistList H = hist_list();
         if (H.n > 0 && !sg_valid) {  // normally produced by the previous iteration's fused gradient kernel
             DotPairs P;
@@ -360,19 +366,20 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         }
         launch_lbfgs_p(n, p.p, H, sc.p, st);
         // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
-        launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
+        const double* alpha_dev = newton ? nullptr : sc.p + SC_ALPHA;  // Newton: initStepSize = 1 (Optimizer.cpp:1088)
+        if (!newton) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
         // ---- back-tracking line search (Optimizer.cpp:752-881): the first trial and everything that follows an accepted
         //      step are enqueued without waiting; the host looks at the result once per iteration ----
         std::swap(x.p, x0.p);  // x0 = current positions
-        launch_axpy_dev(n, x.p, x0.p, p.p, sc.p + SC_ALPHA, 0.0, st);
+        launch_axpy_dev(n, x.p, x0.p, p.p, alpha_dev, 1.0, st);
         launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
         ++evals;
         // gradient at the trial point (g_old is the spare buffer until the step is accepted) + new pair + the next iteration's dots
         const int sl = cfg.history > 0 ? free_slots.back() : -1;  // history+1 buffers: a candidate slot is always free
         launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl,
-                             sc.p + SC_ALPHA, 0.0, H, md_partial.p, counter.p, sc.p, st);
+                             alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p, st);
         fetch_scalars(0, SC_COUNT);
-        double alpha = h_sc[SC_ALPHA], Et = h_sc[SC_E];
+        double alpha = newton ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
         if (Et > E && alpha > 0.0) {
             // rare: halve until the energy does not increase, then redo the gradient / pair at the accepted point
             while (true) {
@@ -405,8 +412,8 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         iter_log.insert(iter_log.end(), {alpha, E, gg});
     } while (gg > target && iters < cfg.max_iters);
     DG_CUDA(cudaEventRecord(ev[1], st));
-    // ---- Hessian refresh at the end of the step (DOTTimeStepper.cpp:343, 349-380) ----
-    refresh();
+    // ---- Hessian refresh at the end of the step (DOTTimeStepper.cpp:343, 349-380); Newton refactorises per iteration instead ----
+    if (!newton) refresh();
     DG_CUDA(cudaEventRecord(ev[2], st));
     // ---- BE update (Optimizer.cpp:354-361) ----
     launch_velocity(nV, vel.p, x.p, xn.p, dt, st);

@@ -94,10 +94,11 @@ def write_msh(path: str, V: np.ndarray, T: np.ndarray, SF: np.ndarray | None = N
 
 def write_script(path: str, msh_path: str, energy: str = "SNH", parts: int = 8, anim: str = "twist",
                  duration: float = 5.0, dt: float = 0.025, density: float = 1000.0,
-                 youngs: float = 1e5, poisson: float = 0.4, tol: float | None = None) -> None:
+                 youngs: float = 1e5, poisson: float = 0.4, tol: float | None = None, stepper: str = "DOT") -> None:
     """A DOT script with the keys the shipped input/*.txt scripts use (reference Config.cpp:43-200)."""
     with open(path, "w") as f:
-        f.write("energy %s\ntimeStepper DOT %d\ninexactSolve 0\nwarmStart 2\nresolution 1000\nsize 1\n" % (energy, parts))
+        ts = "DOT %d" % parts if stepper == "DOT" else stepper  # `timeStepper Newton` = Projected Newton (Config.cpp:76-80)
+        f.write("energy %s\ntimeStepper %s\ninexactSolve 0\nwarmStart 2\nresolution 1000\nsize 1\n" % (energy, ts))
         f.write("time %.17g %.17g\ndensity %.17g\nstiffness %.17g %.17g\nscript %s\n" % (duration, dt, density, youngs, poisson, anim))
         f.write("shape input %s\n" % msh_path)
         if tol is not None:

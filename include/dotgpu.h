@@ -156,6 +156,12 @@ int dotgpu_anim_step(dotgpu_anim* a, double* x_inout, double dt); /* stepAnimScr
  * ------------------------------------------------------------------------------------------ */
 typedef struct dotgpu_stepper dotgpu_stepper;
 
+/* flags of dotgpu_stepper_config */
+#define DOTGPU_FLAG_NEWTON 2 /* Projected Newton instead of DOT: Optimizer::solve_oneStep (Optimizer.cpp:703-749) - the global PD-projected
+                              * Hessian is re-assembled, factorised and solved in EVERY iteration, step length starts at 1 (initStepSize,
+                              * :1076-1093); `timeStepper Newton` scripts, the reference's "1 subdomain" case.  Use num_subdomains = 1,
+                              * epart all 0. */
+
 typedef struct dotgpu_stepper_config {
     int32_t device;
     int32_t energy_type;      /* DOTGPU_ENERGY_* */
@@ -169,7 +175,7 @@ typedef struct dotgpu_stepper_config {
     int32_t rank, world;      /* multi-GPU: subdomains are dealt to ranks; world=1 for one GPU */
     const void* nccl_unique_id; /* ncclUniqueId bytes (128) when world>1, else NULL */
     int32_t target_fixed_count; /* #fixed verts in the tolerance formula; reference uses 1 */
-    int32_t flags;            /* bit0: use CUDA graphs */
+    int32_t flags;            /* DOTGPU_FLAG_* */
 } dotgpu_stepper_config;
 void dotgpu_stepper_default_config(dotgpu_stepper_config* c);
 /* Static map of subdomains to ranks (the multi-GPU sharding of the path): writes the ascending list of

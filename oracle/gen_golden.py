@@ -41,6 +41,11 @@ CASES = [
     ("small_fcr_k3_stretch", "bar_small", "FCR", 3, "stretch", 5, [5], 48, 0.025),
     ("small_snh_k5_tsns_dt24", "bar_small", "SNH", 5, "twistnsns_old", 8, [8], 16, 0.0416667),
 ]
+# Projected Newton (`timeStepper Newton`, Optimizer::solve_oneStep - the reference's "1 subdomain" case): same tuple, parts unused
+PN_CASES = [
+    ("small_fcr_newton_twist", "bar_small", "FCR", 4, "twist", 4, [1, 4], 16, 0.025),
+    ("tiny_snh_newton_tsns", "bar_tiny", "SNH", 4, "twistnsns", 5, [1, 5], -1, 0.025),
+]
 # kernel-level states: name, mesh, energy, parts, perturbation amplitude (x cell size), seed
 KERNEL_CASES = [
     ("tiny_fcr_inverted", "bar_tiny", "FCR", 4, 0.45, 12345),
@@ -73,7 +78,7 @@ def make_mesh(tmp, preset):
     return V, T, msh
 
 
-def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt):
+def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepper="DOT"):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
         V, T, msh = make_mesh(tmp, preset)
@@ -82,10 +87,12 @@ def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt):
         dd = os.path.join(tmp, "dump")
         args = ["--script", script, "--frames", str(frames), "--quiet", "--dump-dir", dd,
                 "--dump-frames", ",".join(map(str, dumps)), "--he-cap", str(he_cap)]
+        if stepper != "DOT":
+            args += ["--stepper", stepper]
         stats = run_ref(args, tmp)
         arrs = collect(dd)
         arrs["iterStats"] = np.array(open(os.path.join(dd, "iterStats.txt")).read())
-        arrs["meta"] = np.array(json.dumps(dict(name=name, preset=preset, energy=energy, parts=parts, anim=anim,
+        arrs["meta"] = np.array(json.dumps(dict(name=name, preset=preset, energy=energy, parts=parts, anim=anim, stepper=stepper,
                                                 frames=frames, dumps=dumps, dt=dt, stats={k: stats[k] for k in
                                                 ("inner_iters", "sumV", "sqnormV", "line_search_halvings", "targetGRes", "frame_iters")})))
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **arrs)
@@ -145,6 +152,9 @@ if __name__ == "__main__":
     for c in CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c)
+    for c in PN_CASES:
+        if not a.only or a.only in c[0]:
+            gen_case(*c, stepper="Newton")
     for c in KERNEL_CASES:
         if not a.only or a.only in c[0]:
             gen_kernel_case(*c)

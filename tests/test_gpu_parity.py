@@ -415,3 +415,41 @@ def test_frames_are_bit_reproducible():
         outs.append((x.copy(), np.concatenate(logs)))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("name", ["small_fcr_newton_twist", "tiny_snh_newton_tsns"])
+def test_projected_newton_follows_reference(name):
+    """Row f1 (Optimizer::solve_oneStep, Optimizer.cpp:703-749; the reference's `timeStepper Newton`, i.e. BASELINE's
+    "1 subdomain" case): the global PD-projected Hessian is re-assembled, factorised (K3/K4/K6) and solved (K5) in every
+    iteration, step length starts at 1.  From the reference's state after frame 1 the GPU run reproduces the reference's
+    iteration counts, its iterStats (printed with 6 digits) and its positions (1e-8).  Frame 1 itself is compared at solver
+    tolerance only: its first Hessian is the (near-)rest-state one, where the reference's 2x2 projection is discontinuous
+    (see tests/test_oracle_golden.py::test_time_stepping_follows_reference_from_restart)."""
+    g = Golden(name)
+    V, T = g["setup/V_rest"], g["setup/F"]
+    a = D.Anim(g.meta["anim"], V)
+    stp = D.Stepper(V, T, np.zeros(T.shape[0], dtype=np.int32), a.fixed_mask(), energy=g.meta["energy"], k=1, dt=g.meta["dt"], newton=True)
+    assert abs(stp.target - g.meta["stats"]["targetGRes"]) <= 1e-12 * stp.target
+    ref_stats = g.iter_stats()
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    # frame 1 from rest: converges to the reference's minimiser within the solver tolerance
+    x = V.copy()
+    a.step(x, g.meta["dt"])
+    fs = stp.frame(x)
+    assert fs.converged == 1 and abs(fs.iters - g.meta["stats"]["frame_iters"][0]) <= 1
+    assert np.abs(x - g["frame%d/V" % f0]).max() < 5e-4
+    # exact path from the reference's state
+    stp.set_state(g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    x = g["frame%d/V" % f0].copy()
+    for f in range(f0 + 1, dumps[-1] + 1):
+        a.step(x, g.meta["dt"])
+        fs = stp.frame(x)
+        ref = ref_stats[ref_stats[:, 0] == f - 1]
+        log = stp.iter_log()
+        assert fs.converged == 1 and fs.iters == g.meta["stats"]["frame_iters"][f - 1], f
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-5, atol=0)   # step sizes
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-5)           # energies
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3)           # |g|^2 (quadratically small at the last iteration)
+        if g.has("frame%d/V" % f):
+            assert np.abs(x - g["frame%d/V" % f]).max() < 1e-8, f
