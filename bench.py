@@ -147,8 +147,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = load_workload(a.workload)
     nT, nV = wl["T"].shape[0], wl["V"].shape[0]
-    config = {"workload": "%s: structured Kuhn bar %d tets / %d nodes, %s, DOT %d subdomains (reference METIS labels), script %s, dt %g, "
-                          "tol 1e-5" % (a.workload, nT, nV, wl["energy"], wl["k"], wl["anim"], DT),
+    method = "Projected Newton (timeStepper Newton)" if wl["newton"] else "DOT %d subdomains (reference METIS labels)" % wl["k"]
+    config = {"workload": "%s: structured Kuhn bar %d tets / %d nodes, %s, %s, script %s, dt %g, "
+                          "tol 1e-5" % (a.workload, nT, nV, wl["energy"], method, wl["anim"], DT),
               "l2": "inputs larger than L2, no explicit flush: every L-BFGS iteration streams the solve panels of all subdomains (2 x nnz(L) x 8 B "
                     "= 271 MB on bar17K_like, 3.0 GB on bar1M vs 126 MB of L2) and every frame rewrites ~4 x that in the Hessian refresh; "
                     "positions / gradients (3 nV doubles) are L2-resident by design",
