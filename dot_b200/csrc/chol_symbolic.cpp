@@ -1,6 +1,7 @@
 #include "chol_symbolic.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 
@@ -16,11 +17,15 @@ struct Graph {
 struct NDOrder {
     const Graph& g;
     int leaf;
+    bool bisector = false;  // second separator candidate; measured on B200: -4 % nnz(L), -8 % flops but one more level and no gain in time
     std::vector<int> stamp, lev, queue;
     int cur_stamp = 0;
     std::vector<std::vector<int>> supers;  // emitted supernodes (node lists), children before parents
 
-    NDOrder(const Graph& g_, int leaf_) : g(g_), leaf(leaf_), stamp(g_.nn, 0), lev(g_.nn, -1) {}
+    NDOrder(const Graph& g_, int leaf_) : g(g_), leaf(leaf_), stamp(g_.nn, 0), lev(g_.nn, -1) {
+        const char* e = std::getenv("DOTGPU_ND_BISECTOR");
+        if (e) bisector = *e == '1';
+    }
 
     // BFS inside the node set marked with `mark` in stamp[]; returns levels in lev[], order in queue
     int bfs(int start, int mark, int visited_mark) {
@@ -56,7 +61,7 @@ struct NDOrder {
         bfs(S[0], m0, m1);
         int far = queue.back();
         int m2 = ++cur_stamp;
-        int nlev = bfs(far, m1, m2);
+        int nlev = bfs(far, m1, m2);  // queue.back() = the other end of the pseudo-diameter
         if (nlev <= 2) {
             supers.push_back(S);
             return;
@@ -87,7 +92,7 @@ struct NDOrder {
                 before += cnt[L];
             }
         }
-        // separator = nodes of level `best` that touch level best+1; the rest of the level stays on the near side
+        // candidate 1: nodes of level `best` that touch level best+1 (the rest of the level stays on the near side)
         std::vector<int> sep;
         int msep = ++cur_stamp;
         for (int v : S) {
@@ -95,9 +100,43 @@ struct NDOrder {
             bool touches = false;
             for (int i = g.ptr[v]; i < g.ptr[v + 1] && !touches; ++i) {
                 int w = g.idx[i];
-                if ((stamp[w] == m2 || stamp[w] == msep) && lev[w] == best + 1) touches = true;
+                if (stamp[w] == m2 && lev[w] == best + 1) touches = true;
             }
             if (touches) sep.push_back(v);
+        }
+        // candidate 2 ("bisector"): distances from BOTH ends of the pseudo-diameter; a node belongs to the end it is closer to,
+        // the separator is the smaller of the two boundary layers.  Level shells around one end are curved; the bisector of two
+        // far-apart ends is close to a plane and usually thinner on blob-shaped subdomains.
+        if (bisector) {
+            std::vector<int> dist_b(S.size());
+            for (size_t i = 0; i < S.size(); ++i) dist_b[i] = lev[S[i]];
+            const int far2 = queue.back();
+            int m3 = ++cur_stamp;
+            bfs(far2, m2, m3);  // lev[] = distance from the other end; all nodes of S now carry stamp m3
+            std::vector<char> side(S.size());
+            int nA = 0;
+            for (size_t i = 0; i < S.size(); ++i) {
+                side[i] = lev[S[i]] < dist_b[i] ? 0 : 1;  // 0: closer to far2
+                nA += side[i] == 0;
+            }
+            const int nB = total - nA;
+            if (nA >= 0.3 * total && nB >= 0.3 * total) {
+                // mark sides through lev[] (0/1) for neighbour tests
+                for (size_t i = 0; i < S.size(); ++i) lev[S[i]] = side[i];
+                std::vector<int> bA, bB;
+                for (size_t i = 0; i < S.size(); ++i) {
+                    const int v = S[i];
+                    bool touches = false;
+                    for (int k = g.ptr[v]; k < g.ptr[v + 1] && !touches; ++k) {
+                        int w = g.idx[k];
+                        if (stamp[w] == m3 && lev[w] != side[i]) touches = true;
+                    }
+                    if (touches) (side[i] == 0 ? bA : bB).push_back(v);
+                }
+                std::vector<int>& cand = bA.size() <= bB.size() ? bA : bB;
+                if (!cand.empty() && cand.size() < sep.size()) sep.swap(cand);
+            }
+            m2 = m3;  // every node of S carries stamp m3 now
         }
         for (int v : sep) stamp[v] = msep;
         // connected components of S \ sep
@@ -164,6 +203,7 @@ void Symbolic::analyze(int n_, const int32_t* ia, const int32_t* ja, int leaf_no
         for (size_t i = 0; i < edges.size(); ++i) g.idx[i] = edges[i].second;  // sorted by (first, second)
     }
     // ---- nested dissection per connected component ----
+    if (const char* e = std::getenv("DOTGPU_ND_LEAF")) leaf_nodes = std::max(2, std::atoi(e));  // experiments
     NDOrder nd(g, leaf_nodes);
     {
         std::vector<char> seen(nn, 0);
