@@ -453,3 +453,43 @@ def test_projected_newton_follows_reference(name):
         assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3)           # |g|^2 (quadratically small at the last iteration)
         if g.has("frame%d/V" % f):
             assert np.abs(x - g["frame%d/V" % f]).max() < 1e-8, f
+
+
+def test_edge_cases_tiny_meshes_and_error_codes():
+    """Edge cases through the C ABI: a one-cell mesh (6 tets) with every vertex but one pinned, a mesh with no Dirichlet
+    vertex at all (null script), a not-positive-definite matrix (status code, no abort), an inverted rest tet (rejected)."""
+    # one cell, 7 of 8 vertices fixed
+    V, T = meshgen.kuhn_bar(1, 1, 1)
+    fm = np.ones(V.shape[0], dtype=np.uint8)
+    fm[-1] = 0
+    stp = D.Stepper(V, T, np.zeros(T.shape[0], dtype=np.int32), fm, energy="FCR", k=1)
+    x = V.copy()
+    fs = stp.frame(x)
+    assert fs.converged == 1 and np.isfinite(x).all() and fs.iters < 50
+    assert np.array_equal(x[fm > 0], V[fm > 0])          # Dirichlet rows stay where the caller put them
+    # free-floating bar under gravity, 3 subdomains: everything falls by g dt^2 in the first frame (no elastic force at rest for FCR)
+    V, T = meshgen.preset("bar_tiny")
+    V = meshgen.normalise_like_loader(V)
+    ep = np.minimum((V[T].mean(axis=1)[:, 0] * 3).astype(np.int32), 2)
+    stp = D.Stepper(V, T, ep, np.zeros(V.shape[0], dtype=np.uint8), energy="FCR", k=3)
+    x = V.copy()
+    fs = stp.frame(x)
+    assert fs.converged == 1
+    assert np.abs((x - V) - np.array([0.0, -9.80665 * 0.025 ** 2, 0.0])).max() < 1e-9
+    # not SPD: reported, not fatal
+    ia = np.array([0, 2, 3], dtype=np.int32)
+    ja = np.array([0, 1, 1], dtype=np.int32)
+    s = D.Solver(ia, ja)
+    s.set_values(np.array([1.0, 2.0, 1.0]))              # [[1,2],[2,1]] is indefinite
+    with pytest.raises(D.DotGpuError) as ei:
+        s.factorize()
+    assert ei.value.code == -4                           # DOTGPU_ERR_NOT_SPD
+    s.set_values(np.array([4.0, 1.0, 3.0]))
+    s.factorize()
+    assert np.allclose(s.solve(np.array([1.0, 2.0])), np.linalg.solve(np.array([[4.0, 1.0], [1.0, 3.0]]), [1.0, 2.0]), rtol=1e-14)
+    # inverted rest tet
+    Vb, Tb = meshgen.kuhn_bar(1, 1, 1)
+    Tb = Tb.copy()
+    Tb[0, [1, 2]] = Tb[0, [2, 1]]
+    with pytest.raises(D.DotGpuError):
+        D.Stepper(Vb, Tb, np.zeros(Tb.shape[0], dtype=np.int32), np.zeros(Vb.shape[0], dtype=np.uint8), energy="SNH", k=1)
