@@ -24,6 +24,7 @@ struct DeviceMesh {
     DevBuf<int> lv_ptr, vp_ptr, vp_idx;
     DevBuf<unsigned short> g_cptr, g_cidx;
     DevBuf<double> gpart;   // 3 doubles per (CTA, local vertex)
+    DevBuf<double> epart;   // elastic energy partial per K2 CTA (energy fused into the gradient pass)
     DevBuf<double> He;      // 90*nT, allocated on first use
     DevBuf<double> partial; // block partial sums for reductions
     int n_partial = 0;
@@ -39,11 +40,12 @@ void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st);
 // g = gather(elemental gradients) [+ m (x - xTilde) on free vertices]; fixed entries zero
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st);
-// gradient + new L-BFGS pair + every inner product of the next iteration's first loop in one pass (see k_grad_vertex_pair)
+// gradient + new L-BFGS pair + every inner product of the next iteration's first loop in one pass (see k_grad_vertex_pair);
+// with_energy: also sc[SC_E] = incremental potential at x (K1 fused into K2: the line search needs both at the same point)
 struct HistList;
 void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
-                          const HistList& H, double* partial, unsigned* counter, double* sc, cudaStream_t st);
+                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st);
 void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st);
 // fills m.He ([nT][10][9])
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st);

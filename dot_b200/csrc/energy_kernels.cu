@@ -129,15 +129,19 @@ __global__ void __launch_bounds__(TPB) k_grad_block(int nT, const int4* __restri
                                                     const double* __restrict__ vol, const double* __restrict__ mu,
                                                     const double* __restrict__ lam, const double* __restrict__ x, double coef,
                                                     const int* __restrict__ lv_ptr, const unsigned short* __restrict__ cptr,
-                                                    const unsigned short* __restrict__ cidx, double* __restrict__ part) {
+                                                    const unsigned short* __restrict__ cidx, double* __restrict__ part,
+                                                    double* __restrict__ epartial) {
     __shared__ double sg[12 * TPB];
+    __shared__ double she[TPB / 32];
     const int t = blockIdx.x * TPB + threadIdx.x;
+    double e_t = 0.0;  // vol_t * Psi_t: the energy of the same state comes for free (K1 fused into K2 inside the iteration)
     if (t < nT) {
         TetIn in;
         load_tet(t, nT, tets, DmInv, vol, mu, lam, x, in);
         Mat3 P;
         double psi;
         first_piola<EN>(in.F, in.mu, in.lam, P, psi);
+        e_t = psi * in.vol;
         const double w = coef * in.vol;
         // g_e[3+3a+b] = w * Dm^-1.row(a) . P.row(b)   (IglUtils.cpp:857-868); corner 0 = -(sum of the others)
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -154,6 +158,10 @@ __global__ void __launch_bounds__(TPB) k_grad_block(int nT, const int4* __restri
         sg[threadIdx.x] = -s0;
         sg[TPB + threadIdx.x] = -s1;
         sg[2 * TPB + threadIdx.x] = -s2;
+    }
+    if (epartial) {  // uniform branch; block_sum contains the barrier that also publishes sg
+        const double se = block_sum<TPB>(e_t, she);
+        if (threadIdx.x == 0) epartial[blockIdx.x] = se;
     }
     __syncthreads();
     const int p0 = lv_ptr[blockIdx.x], nl = lv_ptr[blockIdx.x + 1] - p0;
@@ -209,8 +217,9 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
                                                           const double* __restrict__ pdir, const double* __restrict__ g_old,
                                                           double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                           const double* __restrict__ alpha_dev, double alpha_host, HistList H,
-                                                          double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
-    constexpr int NACC = 3 + 3 * LB_MAXH;  // gg, ys, s.g, then per history pair: s_i.y, s.y_i, s_i.g
+                                                          double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
+                                                          const double* __restrict__ epartial, int n_epartial, double coef) {
+    constexpr int NACC = 4 + 3 * LB_MAXH;  // gg, ys, s.g, inertia energy, then per history pair: s_i.y, s.y_i, s_i.g
     __shared__ double shm[8 * NACC], res[NACC];
     __shared__ bool last;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
@@ -219,14 +228,18 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
     for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
     for (int v = blockIdx.x * 256 + threadIdx.x; v < nV; v += gridDim.x * 256) {
         double gv[3] = {0.0, 0.0, 0.0};
+        const double m = mass[v];
+        double dx[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dx[c] = x[3 * (size_t)v + c] - xt[3 * (size_t)v + c];
+        acc[3] += (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) * m / 2.0;  // inertia energy: ALL vertices (Optimizer.cpp:1204-1211)
         if (!fixed[v]) {
             for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
                 const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
                 gv[0] += p[0]; gv[1] += p[1]; gv[2] += p[2];
             }
-            const double m = mass[v];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gv[c] += m * (x[3 * (size_t)v + c] - xt[3 * (size_t)v + c]);
+            for (int c = 0; c < 3; ++c) gv[c] += m * dx[c];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -245,22 +258,30 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
             for (int j = 0; j < LB_MAXH; ++j)
                 if (j < H.n) {
                     const double si = H.S[j][e];
-                    acc[3 + 3 * j] += si * y;
-                    acc[4 + 3 * j] += s * H.Y[j][e];
-                    acc[5 + 3 * j] += si * gn;
+                    acc[4 + 3 * j] += si * y;
+                    acc[5 + 3 * j] += s * H.Y[j][e];
+                    acc[6 + 3 * j] += si * gn;
                 }
         }
     }
-    const int nacc = 3 + 3 * H.n;
+    const int nacc = 4 + 3 * H.n;
     if (!multi_reduce_256<NACC>(acc, nacc, shm, res, &last, partial, counter)) return;
+    if (epartial && threadIdx.x < 32) {  // E = coef * sum of the per-CTA elastic partials (fixed order) + inertia energy
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n_epartial; i += 32) v += __ldcg(epartial + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) sc[SC_E] = coef * v + res[3];
+    }
     if ((int)threadIdx.x < nacc) {
         const int j = threadIdx.x;
         const double tot = res[j];
         if (j == 0) sc[SC_GG] = tot;
         else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
         else if (j == 2) { if (sl >= 0) sc[SC_SG + sl] = tot; }
+        else if (j == 3) { }
         else {
-            const int h = (j - 3) / 3, kind = (j - 3) % 3, sh_ = H.slot[h];
+            const int h = (j - 4) / 3, kind = (j - 4) % 3, sh_ = H.slot[h];
             if (kind == 0) { if (sl >= 0) sc[SC_SY + 8 * sh_ + sl] = tot; }       // s_h . y_new
             else if (kind == 1) { if (sl >= 0) sc[SC_SY + 8 * sl + sh_] = tot; }  // s_new . y_h
             else sc[SC_SG + sh_] = tot;                                             // s_h . g_new
@@ -460,19 +481,21 @@ void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStr
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st) {
     int nb = ceil_div(m.nT, TPB);
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
-                m.g_cptr.p, m.g_cidx.p, m.gpart.p);
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p, (double*)nullptr);
     k_grad_vertex<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g);
     count_launch();
 }
 
 void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
-                          const HistList& H, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
+                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st) {
     int nb = ceil_div(m.nT, TPB);
+    if (with_energy && m.epart.n < (size_t)nb) m.epart.alloc(nb);
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
-                m.g_cptr.p, m.g_cidx.p, m.gpart.p);
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p, with_energy ? m.epart.p : (double*)nullptr);
     k_grad_vertex_pair<<<multidot_blocks(m.nV), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g, pdir,
-                                                              g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc);
+                                                              g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc,
+                                                              with_energy ? m.epart.p : (const double*)nullptr, nb, coef);
     count_launch();
 }
 

@@ -373,12 +373,12 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         //      step are enqueued without waiting; the host looks at the result once per iteration ----
         std::swap(x.p, x0.p);  // x0 = current positions
         launch_axpy_dev(n, x.p, x0.p, p.p, alpha_dev, 1.0, st);
-        launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
         ++evals;
-        // gradient at the trial point (g_old is the spare buffer until the step is accepted) + new pair + the next iteration's dots
+        // energy AND gradient at the trial point in one pass over the tets (g_old is the spare buffer until the step is accepted)
+        // + new pair + the next iteration's dots
         const int sl = cfg.history > 0 ? free_slots.back() : -1;  // history+1 buffers: a candidate slot is always free
         launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl,
-                             alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p, st);
+                             alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p, true, st);
         fetch_scalars(0, SC_COUNT);  // the one host round trip of an iteration (measured: ~14 us of 240 on bar17K_like)
         double alpha = newton ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
         if (Et > E && alpha > 0.0) {
@@ -393,7 +393,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                 if (!(Et > E)) break;
             }
             launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, nullptr,
-                                 alpha, H, md_partial.p, counter.p, sc.p, st);
+                                 alpha, H, md_partial.p, counter.p, sc.p, false, st);
             fetch_scalars(0, SC_COUNT);
         }
         E = Et;
