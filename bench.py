@@ -300,7 +300,14 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         r_cpu = run_reference(wl, a.cpu_frames, 0)
         if r_cpu and "error" not in r_cpu:
-            cpu = {"value": r_cpu["fps"], "unit": "frames/s", "cores": r_cpu["cores"], "kind": "reference",
+            one = None
+            try:  # scaling context: the same reference on ONE host thread, short sample
+                r1 = run_reference(wl, max(2, a.cpu_frames // 6), 0, threads=1)
+                if r1 and "error" not in r1:
+                    one = {"value": r1["fps"], "frames": r1["frames"], "inner_iters": r1["inner_iters"]}
+            except Exception:
+                one = None
+            cpu = {"value": r_cpu["fps"], "unit": "frames/s", "cores": r_cpu["cores"], "kind": "reference", "one_thread": one,
                    "sample": "first %d frames of the same workload from rest (%.1f s of CPU work incl. %.1f s set-up); unmodified reference, OpenMP shim "
                              "for TBB, CHOLMOD 3.0.12 + OpenBLAS (1 thread per solver)" % (r_cpu["frames"], r_cpu["wall_sec"], r_cpu["setup_sec"]),
                    "inner_iters": r_cpu["inner_iters"], "ms_per_iter": 1e3 * r_cpu["frames"] / r_cpu["fps"] / max(r_cpu["inner_iters"], 1)}
