@@ -302,7 +302,7 @@ class Stepper:
     (Optimizer::solve_oneStep, the reference's `timeStepper Newton`)."""
 
     def __init__(self, V_rest, tets, epart, fixed_mask, energy="SNH", k=None, dt=0.025, device=0, rel_tol=1e-5, YM=1e5, PR=0.4,
-                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000, newton=False):
+                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000, newton=False, gravity=(0.0, -9.80665, 0.0)):
         V = _f64(V_rest)
         T = _i32(tets)
         ep = _i32(epart)
@@ -318,6 +318,8 @@ class Stepper:
         cfg.YM, cfg.PR, cfg.rho = YM, PR, rho
         cfg.max_iters = max_iters
         cfg.rank, cfg.world = rank, world
+        for i in range(3):
+            cfg.gravity[i] = float(gravity[i])
         if newton:
             cfg.flags |= 2  # DOTGPU_FLAG_NEWTON
         self._id = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
@@ -325,6 +327,10 @@ class Stepper:
         self.cfg = cfg
         self.h = C.c_void_p()
         _chk(lib().dotgpu_stepper_create(C.byref(self.h), C.byref(cfg), self.nV, self.nT, _p(V), _p(T), _p(ep), _p(_u8(fixed_mask))))
+
+    def set_rel_tol(self, rel_tol):
+        """Optimizer::setRelGL2Tol: tolerance of the following time steps."""
+        _chk(lib().dotgpu_stepper_set_rel_tol(self.h, C.c_double(rel_tol)))
 
     def close(self):
         if self.h:

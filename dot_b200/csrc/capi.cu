@@ -573,6 +573,12 @@ int dotgpu_stepper_get_target(dotgpu_stepper* s, double* target) {
     *target = s->s.target;
     return DOTGPU_OK;
 }
+int dotgpu_stepper_set_rel_tol(dotgpu_stepper* s, double rel_tol) {
+    if (!s || !(rel_tol > 0.0)) return DOTGPU_ERR_INVALID;
+    s->s.cfg.rel_tol = rel_tol;
+    s->s.target = s->s.compute_target();
+    return DOTGPU_OK;
+}
 int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* ms_out) {
     API_BEGIN
     DG_REQUIRE(s && ms_out, "null argument");

@@ -223,6 +223,9 @@ int dotgpu_stepper_get_dd(dotgpu_stepper* s, dotgpu_dd** dd_out); /* borrowed po
 int dotgpu_stepper_precondition(dotgpu_stepper* s, const double* q, double* p_out);
 int dotgpu_stepper_eval(dotgpu_stepper* s, const double* x, double* E_out, double* g_out);
 int dotgpu_stepper_get_target(dotgpu_stepper* s, double* target);
+/* Optimizer::setRelGL2Tol (Optimizer.cpp:222-228): relative tolerance of the following time steps (scripts give one per frame
+ * through `tol`, main.cpp:108-117); recomputes targetGRes.  Host-only, no device work. */
+int dotgpu_stepper_set_rel_tol(dotgpu_stepper* s, double rel_tol);
 /* device-only timing helpers for bench.py: run `reps` energy+gradient evaluations (K1+K2) / Hessian
  * refreshes (K3+K4+factor) / preconditioner applications (K5) on resident data, return avg ms by CUDA events */
 int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* ms_out);

@@ -1,0 +1,94 @@
+"""Host-side file formats (dot_b200/io.py): the reference's script format, .msh dialect, restart files, label.obj, and the
+fallback partitioner.  Pure CPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from dot_b200 import io, meshgen
+
+REF = "/root/reference"
+
+
+def test_script_parser_keys(tmp_path):
+    p = tmp_path / "s.txt"
+    p.write_text("energy SNH\ntimeIntegration BE\ntimeStepper DOT 16\ninexactSolve 0\nwarmStart 2\nresolution 1000\nsize 2.5\n"
+                 "time 10 0.0416667\ndensity 1200\nstiffness 2e5 0.45\nturnOffGravity\nscript twistnsns_old\nhandleRatio 0.02\n"
+                 "rotateModel 0 1 0 90\ntuning 2\n1 2\nshape input input/tetMeshes/x.msh\ntol 3\n1e-3 1e-4\n1e-5\nview orthographic\nzoom 0.8\n")
+    s = io.parse_script(str(p))
+    assert (s.energy, s.time_stepper, s.partitions) == ("SNH", "DOT", 16)
+    assert (s.size, s.duration, s.dt, s.rho, s.YM, s.PR) == (2.5, 10.0, 0.0416667, 1200.0, 2e5, 0.45)
+    assert not s.with_gravity and s.script == "twistnsns_old" and s.handle_ratio == 0.02
+    assert s.rot_axis == (0.0, 1.0, 0.0) and s.rot_deg == 90.0
+    assert s.input_shape_path == "input/tetMeshes/x.msh"
+    assert s.tol == [1e-3, 1e-4, 1e-5] and s.rel_tol(0) == 1e-3 and s.rel_tol(7) == 1e-5
+    assert s.num_frames() == 240 and s.unknown == []
+    # k < 2 is rewritten to 4 (Config.cpp:76-80); negative k means block-size mode
+    p.write_text("timeStepper DOT 1\n")
+    assert io.parse_script(str(p)).partitions == 4
+    p.write_text("timeStepper DOT -1 900\n")
+    assert io.parse_script(str(p)).block_size == 900
+    p.write_text("timeStepper Newton\nenergy FCR\n")
+    assert io.parse_script(str(p)).time_stepper == "Newton" and io.parse_script(str(p)).rel_tol(3) == 1e-5
+    p.write_text("timeStepper ADMM 10\n")
+    with pytest.raises(ValueError):
+        io.parse_script(str(p))
+
+
+def test_msh_and_status_round_trip(tmp_path):
+    V, T = meshgen.preset("bar_tiny")
+    meshgen.write_msh(str(tmp_path / "m.msh"), V, T)
+    V2, T2, SF = io.read_msh(str(tmp_path / "m.msh"))
+    assert np.array_equal(V, V2) and np.array_equal(T, T2)          # %.17g round-trips doubles exactly
+    assert np.array_equal(SF, meshgen.surface_tris(T))
+    s2t = io.surface_to_tet(T, SF)
+    assert all(set(SF[i]).issubset(set(T[s2t[i]])) for i in range(SF.shape[0]))
+    io.write_label_obj(str(tmp_path / "label.obj"), SF, s2t, np.arange(T.shape[0]) % 3)
+    lines = open(tmp_path / "label.obj").read().splitlines()
+    assert len(lines) == SF.shape[0] and lines[0].split()[0] == "v"
+    rng = np.random.default_rng(0)
+    x, v = rng.standard_normal(V.shape), rng.standard_normal(3 * V.shape[0])
+    io.write_status(str(tmp_path / "status7"), 7, x, v)
+    st = io.read_status(str(tmp_path / "status7"))
+    assert st["timestep"] == 7
+    assert np.allclose(st["position"], x, rtol=1e-6) and np.allclose(st["velocity"], v, rtol=1e-6)   # %le keeps 7 digits, like the reference
+    assert st["dx_Elastic"].shape == x.shape
+    w = io.IterStatsWriter(str(tmp_path / "iterStats.txt"))
+    w.frame(0, np.array([[0.0, 1.5, 2.5], [1.0, 1.25, 1e-9]]))
+    w.close()
+    assert open(tmp_path / "iterStats.txt").read().splitlines() == ["0 0 1.5 2.5 0", "0 1 1.25 1e-09 0"]
+
+
+def test_rotate_model_matches_axis_angle():
+    V = np.array([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0]])
+    R = io.rotate_model(V, (0.0, 0.0, 1.0), 90.0)
+    assert np.allclose(R, [[0.0, 1.0, 0.0], [-2.0, 0.0, 0.0]], atol=1e-15)
+    assert io.rotate_model(V, (0, 0, 1), 0.0) is V
+
+
+def test_rcb_partition_is_balanced_and_complete():
+    V, T = meshgen.preset("bar2K")
+    for k in (1, 3, 8, 13):
+        ep = io.partition_rcb(V, T, k)
+        cnt = np.bincount(ep, minlength=k)
+        assert ep.min() == 0 and ep.max() == k - 1 and cnt.min() > 0
+        assert cnt.max() - cnt.min() <= max(2, 0.02 * T.shape[0])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "input")), reason="reference inputs only exist in the build container")
+def test_reference_scripts_and_meshes_parse():
+    ok = 0
+    for f in sorted(glob.glob(os.path.join(REF, "input", "*.txt")) + glob.glob(os.path.join(REF, "input", "tb*", "*.txt"))):
+        try:
+            s = io.parse_script(f)
+        except ValueError:
+            continue                                   # steppers / energies outside the GPU path
+        assert s.unknown == [], (f, s.unknown)
+        assert s.dt > 0 and s.YM > 0
+        ok += 1
+    assert ok >= 40                                 # every shipped DOT script except the rubberBandPull ones
+    V, T, SF = io.read_msh(os.path.join(REF, "input", "tetMeshes", "bunny5K.msh"))
+    assert (V.shape[0], T.shape[0]) == (4670, 19379) and SF.shape[0] > 0       # bunny5K sizes
+    Dm = np.stack([V[T[:, 1]] - V[T[:, 0]], V[T[:, 2]] - V[T[:, 0]], V[T[:, 3]] - V[T[:, 0]]], axis=2)
+    assert (np.linalg.det(Dm) > 0).all()
