@@ -822,3 +822,84 @@ class DOTStepper:
         self.x_n = self.x.copy()
         self.compute_xtilde()
         return it
+
+
+# ---------------------------------------------------------------------------------------
+# f1  Projected Newton: Optimizer::fullyImplicit / solve_oneStep (Optimizer.cpp:654-749), the reference's
+#     `timeStepper Newton` ("1 subdomain" in BASELINE.json)
+# ---------------------------------------------------------------------------------------
+class NewtonStepper:
+    """Each iteration: PD-projected Hessian of the incremental potential at the current iterate (computePrecondMtr,
+    Optimizer.cpp:1257-1308), factorise, p = -H^-1 g, line search from step 1 (initStepSize, :1088) halving while the energy
+    increases (:752-833), new gradient.  Stops when |g|^2 <= targetGRes."""
+
+    def __init__(self, mesh: Mesh, energy, anim_kind="twist", dt=0.025, handle_ratio=0.01, rel_tol=1e-5):
+        self.mesh, self.energy, self.dt = mesh, energy, dt
+        self.x = mesh.V_rest.copy()
+        self.anim = AnimScripter(anim_kind, mesh.V_rest, border_verts(mesh.V_rest, handle_ratio))
+        self.fixed = self.anim.fixed()
+        self.fixed_mask = np.zeros(mesh.nV, dtype=bool)
+        self.fixed_mask[self.fixed] = True
+        self.gia, self.gja = set_pattern(mesh.v_neighbor(), self.fixed)
+        self.gravity = np.array([0.0, -9.80665, 0.0])
+        self.vel = np.zeros_like(self.x)
+        self.x_n = self.x.copy()
+        self.target = target_gres(energy, mesh, dt, rel_tol)
+        self.compute_xtilde()
+        self.inner_iters = 0
+        self.halvings = 0
+        self.log = []
+
+    compute_xtilde = DOTStepper.compute_xtilde
+    energy_at = DOTStepper.energy_at
+
+    def restart(self, frames_done, x, vel):
+        dummy = self.mesh.V_rest.copy()
+        self.anim = AnimScripter(self.anim.kind, self.mesh.V_rest, self.anim.handles)
+        for _ in range(frames_done):
+            dummy = self.anim.step(dummy, self.dt)
+        self.x = np.array(x, dtype=float, copy=True)
+        self.x_n = self.x.copy()
+        self.vel = np.array(vel, dtype=float).reshape(-1, 3).copy()
+        self.compute_xtilde()
+        self.log = []
+
+    def hessian(self, svd):
+        F, U, s, V = svd
+        He = elem_hessians(self.energy, self.mesh, U, s, V, self.dt ** 2, True)
+        return fill_global(self.mesh, He, self.gia, self.gja, self.fixed_mask)
+
+    def step_frame(self):
+        mesh, dt = self.mesh, self.dt
+        self.x = self.anim.step(self.x, dt)
+        d = self.vel * dt + self.gravity * dt * dt                       # initX(2)
+        d[self.fixed_mask] = 0.0
+        self.x = self.x + 1.0 * d
+        E, _, svd = self.energy_at(self.x)
+        g, _, _ = full_gradient(self.energy, mesh, self.x, self.xTilde, dt, self.fixed_mask, svd)
+        self.log.append((0.0, E, float(g @ g)))
+        it = 0
+        while True:
+            a = self.hessian(svd)
+            p = spla.splu(csr_upper_to_full(self.gia, self.gja, a)).solve(-g)
+            alpha = 1.0
+            x0 = self.x
+            while True:
+                xt = x0 + alpha * p.reshape(-1, 3)
+                Et, _, svd = self.energy_at(xt)
+                if not (Et > E and alpha > 0.0):
+                    break
+                alpha /= 2.0
+                self.halvings += 1
+            self.x, E = xt, Et
+            g, _, _ = full_gradient(self.energy, mesh, self.x, self.xTilde, dt, self.fixed_mask, svd)
+            self.inner_iters += 1
+            it += 1
+            gg = float(g @ g)
+            self.log.append((alpha, E, gg))
+            if gg <= self.target or it >= 10000:
+                break
+        self.vel = (self.x - self.x_n) / dt
+        self.x_n = self.x.copy()
+        self.compute_xtilde()
+        return it

@@ -187,3 +187,30 @@ def test_time_stepping_from_rest(name):
         assert stp.log[-1][2] <= stp.target
         if g.has("frame%d/V" % f):
             assert np.abs(stp.x - g["frame%d/V" % f]).max() < 2e-4, f
+
+
+@pytest.mark.parametrize("name", ["small_fcr_newton_twist", "tiny_snh_newton_tsns"])
+def test_projected_newton_follows_reference_from_restart(name):
+    """Row f1: the oracle's Projected Newton (Optimizer::solve_oneStep) against the reference's `timeStepper Newton` run,
+    from the reference's state after frame 1 (frame 1 starts from the rest-state Hessian whose projection is
+    rounding-dependent, see test_time_stepping_follows_reference_from_restart): same iteration counts, same iterStats
+    (6 printed digits), positions to 1e-8."""
+    g = Golden(name)
+    m = mesh_of(g)
+    stp = O.NewtonStepper(m, g.meta["energy"], g.meta["anim"], g.meta["dt"])
+    assert abs(stp.target - g.meta["stats"]["targetGRes"]) <= 1e-12 * stp.target
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    stp.restart(f0, g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    assert np.abs(stp.xTilde - g["frame%d/xTilta" % f0]).max() < 1e-15
+    for f in range(f0 + 1, dumps[-1] + 1):
+        stp.log = []
+        it = stp.step_frame()
+        ref = _frame_rows(g, f)
+        log = np.asarray(stp.log)
+        assert it == g.meta["stats"]["frame_iters"][f - 1], f
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-5, atol=0)
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-5)
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3)
+        if g.has("frame%d/V" % f):
+            assert np.abs(stp.x - g["frame%d/V" % f]).max() < 1e-8, f
