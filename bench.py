@@ -3,12 +3,15 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-A "step" is one converged time step (frame) of the scripted twist.  Default workload = BASELINE config C2:
-the bar17K-sized synthetic bar (86,400 tets / 16,640 nodes), Stable Neo-Hookean, 8 METIS subdomains, dt=0.025
-(the reference's bar17K.msh lives only under /root/reference/input, so the mesh is the structured Kuhn bar of
-dot_b200/meshgen.py; its METIS labels were produced by the reference's own wrapper and are committed under
-tests/golden/).  Other workloads: bar5K_like (C1 size, FCR k=6), bar136K_like (C3 size, FCR k=64), bar1M (C4,
-SNH k=128).
+A "step" is one converged time step (frame) of the scripted boundary motion.  Default workload = BASELINE config C4:
+the synthetic 1M-tet bar twist (1,029,000 tets / 182,736 nodes), Stable Neo-Hookean, 128 METIS subdomains, dt=0.025 -
+the largest single-GPU configuration and the one north_star's scaling target names.  The same line carries a
+`secondary` record for config C2 on the reference's own mesh (bar17K.msh: 86,058 tets, SNH, 8 subdomains; fixture
+tests/golden/mesh_bar17K.npz) and `parity` objects: both arms (this library and the unmodified reference binary) run the
+same script from rest at a tight tolerance and the positions are compared.  METIS labels of every workload were produced by
+the reference's own wrapper and are committed under tests/golden/.  Other workloads: bunny5K (C1: FCR k=6 twistnsns, and
+bunny5K_PN = Projected Newton), horse38K_tb4 (C5: SNH, dt=1/24, k=16, twistnsns_old), bar17K_like / bar5K_like /
+bar136K_like (structured stand-ins of round 1).
 
 JSON line: value = frames/s with positions resident on the device (only the scripted Dirichlet targets travel),
 e2e = frames/s through dotgpu_stepper_frame with host positions in and out every frame, roofline = the dominant
@@ -32,28 +35,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (mesh preset, energy, subdomains, anim)
-    "bar17K_like": ("bar17K_like", "SNH", 8, "twist"),
-    "bar5K_like": ("bar5K_like", "FCR", 6, "twist"),
-    "bar136K_like": ("bar136K_like", "FCR", 64, "twist"),
-    "bar1M": ("bar1M", "SNH", 128, "twist"),
-    # BASELINE config C1 ("1 subdomain" = the reference's `timeStepper Newton`): Projected Newton, FCR
-    "bar5K_like_PN": ("bar5K_like", "FCR", 1, "twist"),
+    # name: (mesh preset or fixture, energy, subdomains, anim, dt)
+    "bar1M": ("bar1M", "SNH", 128, "twist", 0.025),                      # C4 (default)
+    "bar17K": ("bar17K", "SNH", 8, "twist", 0.025),                      # C2 on the reference's own mesh
+    "bunny5K": ("bunny5K", "FCR", 6, "twistnsns", 0.025),                # C1 as shipped (DOT 6)
+    "bunny5K_PN": ("bunny5K", "FCR", 1, "twistnsns", 0.025),             # C1 "1 subdomain" = `timeStepper Newton`
+    "horse38K_tb4": ("horse38K", "SNH", 16, "twistnsns_old", 0.0416667), # C5 (extreme deformation, halving-bound)
+    "bar17K_like": ("bar17K_like", "SNH", 8, "twist", 0.025),
+    "bar5K_like": ("bar5K_like", "FCR", 6, "twist", 0.025),
+    "bar136K_like": ("bar136K_like", "FCR", 64, "twist", 0.025),
+    "bar5K_like_PN": ("bar5K_like", "FCR", 1, "twist", 0.025),
 }
-DT = 0.025
+# the reference arm / CPU legs are bounded samples: at most this many (warm-up, timed) frames per workload size
+CPU_FRAME_CAP = {"bar1M": (1, 3), "bar136K_like": (1, 4), "horse38K_tb4": (1, 4)}
 
 
 def load_workload(name):
     from dot_b200 import meshgen
-    preset, energy, k, anim = WORKLOADS[name]
-    V, T = meshgen.preset(preset)
+    preset, energy, k, anim, dt = WORKLOADS[name]
+    if preset in meshgen.PRESETS:
+        V, T = meshgen.preset(preset)
+        kind = "structured Kuhn bar"
+    else:
+        V, T = meshgen.load_mesh_npz(os.path.join(ROOT, "tests", "golden", "mesh_%s.npz" % preset))
+        kind = "the reference's input/tetMeshes/%s.msh" % preset
     Vn = meshgen.normalise_like_loader(V)
     newton = name.endswith("_PN")
     if newton:
         ep = np.zeros(T.shape[0], dtype=np.int32)
     else:
         ep = np.load(os.path.join(ROOT, "tests", "golden", "labels_%s_k%d.npz" % (preset, k)))["epart"].astype(np.int32)
-    return dict(name=name, preset=preset, energy=energy, k=k, anim=anim, V_raw=V, V=Vn, T=T, epart=ep, newton=newton)
+    return dict(name=name, preset=preset, energy=energy, k=k, anim=anim, dt=dt, V_raw=V, V=Vn, T=T, epart=ep, newton=newton, kind=kind)
 
 
 def peaks():
@@ -92,8 +104,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def run_reference(wl, steps, warmup, threads=None):
-    """The unmodified reference CPU path (oracle/_ref/dot_ref) on the same mesh / script; times frames warmup+1..warmup+steps."""
+def run_reference(wl, steps, warmup, threads=None, tol=None, want_V=False):
+    """The unmodified reference CPU path (oracle/_ref/dot_ref) on the same mesh / script; times frames warmup+1..warmup+steps.
+    tol: relative tolerance override (parity runs use a tight one); want_V: also return the final positions."""
     from dot_b200 import meshgen
     exe = os.path.join(ROOT, "oracle", "_ref", "dot_ref")
     if not os.path.exists(exe):
@@ -102,7 +115,7 @@ def run_reference(wl, steps, warmup, threads=None):
     msh = os.path.join(tmp, "mesh.msh")
     meshgen.write_msh(msh, wl["V_raw"], wl["T"])
     script = os.path.join(tmp, "script.txt")
-    meshgen.write_script(script, msh, energy=wl["energy"], parts=wl["k"], anim=wl["anim"], dt=DT, stepper="Newton" if wl["newton"] else "DOT")
+    meshgen.write_script(script, msh, energy=wl["energy"], parts=wl["k"], anim=wl["anim"], dt=wl["dt"], stepper="Newton" if wl["newton"] else "DOT")
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
     blas = os.path.join(ROOT, "oracle", "_ref", "blasdir.txt")
     if os.path.exists(blas):
@@ -110,16 +123,25 @@ def run_reference(wl, steps, warmup, threads=None):
     cores = threads or os.cpu_count() or 1
     env["OMP_NUM_THREADS"] = str(cores)
     t0 = time.time()
-    out = subprocess.run([exe, "--script", script, "--frames", str(warmup + steps), "--quiet", "--threads", str(cores)], cwd=tmp, env=env,
-                         capture_output=True, text=True)
+    cmd = [exe, "--script", script, "--frames", str(warmup + steps), "--quiet", "--threads", str(cores)]
+    if tol is not None:
+        cmd += ["--tol", repr(tol)]
+    if want_V:
+        cmd += ["--final-V", os.path.join(tmp, "finalV.npy")]
+    out = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True)
     if out.returncode != 0:
         return {"error": out.stderr[-400:]}
     js = [l for l in out.stdout.splitlines() if l.startswith("{")]
     st = json.loads(js[-1])
     sec = st["frame_sec"][warmup:]
-    return {"fps": len(sec) / sum(sec), "sec_per_frame": sum(sec) / len(sec), "cores": int(st["threads"]), "frames": len(sec),
-            "inner_iters": int(sum(st["frame_iters"][warmup:])), "setup_sec": st["setup_sec"], "wall_sec": time.time() - t0,
-            "timers_sec": st["timers_sec"], "sumV": st["sumV"]}
+    r = {"fps": len(sec) / sum(sec), "sec_per_frame": sum(sec) / len(sec), "cores": int(st["threads"]), "frames": len(sec),
+         "inner_iters": int(sum(st["frame_iters"][warmup:])), "setup_sec": st["setup_sec"], "wall_sec": time.time() - t0,
+         "timers_sec": st["timers_sec"], "sumV": st["sumV"], "halvings": st["line_search_halvings"], "frame_iters": st["frame_iters"]}
+    if want_V:
+        r["V"] = np.load(os.path.join(tmp, "finalV.npy"))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return r
 
 
 def _emit(line):
@@ -131,35 +153,191 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def workload_config(name, wl, steps, warmup, world):
+    nT, nV = wl["T"].shape[0], wl["V"].shape[0]
+    method = "Projected Newton (timeStepper Newton)" if wl["newton"] else "DOT %d subdomains (reference METIS labels)" % wl["k"]
+    return {"workload": "%s: %s, %d tets / %d nodes, %s, %s, script %s, dt %g, tol 1e-5"
+                        % (name, wl["kind"], nT, nV, wl["energy"], method, wl["anim"], wl["dt"]),
+            "l2": "inputs larger than L2, no explicit flush: every L-BFGS iteration streams the solve panels of all subdomains (2 x nnz(L) x 8 B "
+                  "= 3.0 GB on bar1M, 0.2 GB on bar17K vs 126 MB of L2) and every frame rewrites ~4 x that in the Hessian refresh; "
+                  "positions / gradients (3 nV doubles) are L2-resident by design",
+            "subdomains": wl["k"], "tets": nT, "nodes": nV, "energy": wl["energy"], "frames_timed": steps, "frames_warmup": warmup,
+            "parallelism": "%d GPU(s): subdomains (factor + solves) and tets (energy / gradient / Hessians) sharded by subdomain, balanced by nnz(L); "
+                           "search direction and gradient reduced across ranks every L-BFGS iteration" % world}
+
+
+class Ctx:
+    """Process-wide plumbing: torch.distributed for the rendezvous, barrier and max-over-ranks; everything timed runs in libdotgpu."""
+
+    def __init__(self):
+        import torch
+        import dot_b200 as D
+        self.torch, self.D = torch, D
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def fresh_nccl_id(self):
+        """Every communicator needs its own ncclUniqueId: rank 0 creates one, torch.distributed broadcasts the 128 bytes."""
+        if self.world == 1:
+            return None
+        torch = self.torch
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if self.rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(self.D.nccl_unique_id()), dtype=torch.uint8))
+        torch.distributed.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.torch.distributed.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        tt = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.torch.distributed.all_reduce(tt, op=self.torch.distributed.ReduceOp.MAX)
+        return [float(v) for v in tt]
+
+    def make(self, wl, rel_tol=1e-5):
+        return self.D.Stepper(wl["V"], wl["T"], wl["epart"], self.D.Anim(wl["anim"], wl["V"]).fixed_mask(), energy=wl["energy"], k=wl["k"],
+                              dt=wl["dt"], device=self.local_rank, rank=self.rank, world=self.world, nccl_id=self.fresh_nccl_id(),
+                              newton=wl["newton"], rel_tol=rel_tol)
+
+
+def gpu_frames(ctx, wl, steps, warmup, profile_mode=False, with_kernels=True, with_e2e=True):
+    """value (resident positions), e2e (host positions in/out every frame), per-kernel times, K5 roofline inputs."""
+    D, torch = ctx.D, ctx.torch
+    nT, nV = wl["T"].shape[0], wl["V"].shape[0]
+    dt = wl["dt"]
+    anim0 = D.Anim(wl["anim"], wl["V"])
+    fixed_idx = np.nonzero(anim0.fixed_mask())[0].astype(np.int32)
+    t_setup = time.time()
+    stp = ctx.make(wl)
+    t_setup = time.time() - t_setup
+    an = D.Anim(wl["anim"], wl["V"])
+    x = wl["V"].copy()
+    for f in range(warmup):
+        an.step(x, dt)
+        stp.frame_resident(fixed_idx, x[fixed_idx])
+        x[:] = stp.get_state()[0]
+    ctx.barrier()
+    l0 = stp.launch_count()
+    t0 = time.perf_counter()
+    acc = dict(iters=0, halv=0, dev_ms=0.0, solve_ms=0.0, refresh_ms=0.0, pc_ms=0.0, pc_calls=0, conv=True)
+    for f in range(steps):
+        # the scripted handle motion only needs the handle rows, which the solve leaves where the script put them
+        an.step(x, dt)
+        st = stp.frame_resident(fixed_idx, x[fixed_idx])
+        acc["iters"] += st.iters
+        acc["halv"] += st.halvings
+        acc["dev_ms"] += st.ms_total
+        acc["solve_ms"] += st.ms_solve
+        acc["refresh_ms"] += st.ms_refresh
+        acc["pc_ms"] += st.ms_precond
+        acc["pc_calls"] += st.precond_calls
+        acc["conv"] = acc["conv"] and bool(st.converged)
+    ctx.barrier()
+    t_value = time.perf_counter() - t0
+    launches = stp.launch_count() - l0
+    t_value, acc["dev_ms"], acc["pc_ms"] = ctx.max_over_ranks([t_value, acc["dev_ms"], acc["pc_ms"]])
+    x_final = stp.get_state()[0]
+    out = dict(acc, t_value=t_value, launches=launches, setup_sec=t_setup, nT=nT, nV=nV)
+    owned = stp.owned()
+    infos = [stp.solver_info(s) for s in owned]
+    out["nnz_l"] = sum(i.nnz_l for i in infos)
+    out["n_sub"] = sum(i.n for i in infos)
+    out["flops"] = sum(i.flops for i in infos)
+    out["owned_subdomains"] = len(owned)
+    if with_kernels:
+        # per-kernel device times on the final state (CUDA events on the stepper's stream)
+        names = ["energy", "gradient", "elem_hessians", "fill", "factorize", "precondition", "dot"]
+        out["kms"] = {n: stp.time_kernels(i, 1 if profile_mode else 20) for i, n in enumerate(names)}
+    del stp
+    if with_e2e:
+        # e2e: host positions in / out every frame through dotgpu_stepper_frame (pinned host buffer)
+        stp = ctx.make(wl)
+        an = D.Anim(wl["anim"], wl["V"])
+        pinned = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
+        xe = pinned.numpy()
+        xe[:] = wl["V"]
+        for f in range(warmup):
+            an.step(xe, dt)
+            stp.frame(xe)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for f in range(steps):
+            an.step(xe, dt)
+            st = stp.frame(xe)
+        out["loss"] = float(st.E)       # device->host read of the step's result (energy) is part of frame()
+        ctx.barrier()
+        out["t_e2e"] = ctx.max_over_ranks([time.perf_counter() - t0])[0]
+        out["e2e_vs_resident"] = float(np.abs(xe - x_final).max())
+        del stp
+    return out
+
+
+def parity_run(ctx, wl, frames, tol):
+    """Both arms from rest with the same script at a tight tolerance (with identical partition and start, tol 1e-9,
+    max |dx| / bbox <= 1e-6 per frame); the longest bounding-box edge is 1 after the loader's normalisation.  The reference
+    (oracle/_ref/dot_ref, the checker) runs on rank 0 only."""
+    D = ctx.D
+    stp = ctx.make(wl, rel_tol=tol)
+    an = D.Anim(wl["anim"], wl["V"])
+    x = wl["V"].copy()
+    it = hv = 0
+    conv = True
+    for f in range(frames):
+        an.step(x, wl["dt"])
+        st = stp.frame(x)
+        it += st.iters
+        hv += st.halvings
+        conv = conv and bool(st.converged)
+    del stp
+    ctx.barrier()
+    if ctx.rank != 0:
+        return None
+    r = run_reference(wl, frames, 0, tol=tol, want_V=True)
+    if not r or "error" in r:
+        return {"error": (r or {}).get("error", "oracle/_ref/dot_ref missing")}
+    return {"max_abs_dx_over_bbox": float(np.abs(x - r["V"]).max()), "frames": frames, "tol": tol, "iters_gpu": it, "iters_ref": r["inner_iters"],
+            "halvings_gpu": hv, "halvings_ref": r["halvings"], "all_frames_converged_gpu": conv, "n_gpus": ctx.world,
+            "reference": "unmodified reference binary, same script from rest, %d host threads" % r["cores"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="bar17K_like", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="bar1M", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="dotgpu", choices=["dotgpu", "reference"])
-    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample (~10 s of CPU work on bar17K_like)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU-baseline sample (0: sized per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-C2 record (bar17K) carried next to the main workload")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="for runs under ncu: skip the per-kernel micro-timings (few launches)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = load_workload(a.workload)
     nT, nV = wl["T"].shape[0], wl["V"].shape[0]
-    method = "Projected Newton (timeStepper Newton)" if wl["newton"] else "DOT %d subdomains (reference METIS labels)" % wl["k"]
-    config = {"workload": "%s: structured Kuhn bar %d tets / %d nodes, %s, %s, script %s, dt %g, "
-                          "tol 1e-5" % (a.workload, nT, nV, wl["energy"], method, wl["anim"], DT),
-              "l2": "inputs larger than L2, no explicit flush: every L-BFGS iteration streams the solve panels of all subdomains (2 x nnz(L) x 8 B "
-                    "= 271 MB on bar17K_like, 3.0 GB on bar1M vs 126 MB of L2) and every frame rewrites ~4 x that in the Hessian refresh; "
-                    "positions / gradients (3 nV doubles) are L2-resident by design",
-              "subdomains": wl["k"], "tets": nT, "nodes": nV, "energy": wl["energy"], "frames_timed": a.steps, "frames_warmup": a.warmup,
-              "parallelism": "subdomains dealt round-robin to %d GPU(s); replicated per-tet kernels; one NCCL all-reduce of the search direction per L-BFGS iteration" % world}
+    config = workload_config(a.workload, wl, a.steps, a.warmup, world)
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        r = run_reference(wl, a.steps, a.warmup)
+        # bounded sample: the reference needs ~15 s per frame on the 1M-tet bar (+ ~30 s of std::map-heavy set-up)
+        capw, caps = CPU_FRAME_CAP.get(a.workload, (a.warmup, a.steps))
+        w, k = min(a.warmup, capw), min(a.steps, caps)
+        r = run_reference(wl, k, w)
         if r is None or "error" in r:
             _emit({"impl": "reference", "unavailable": "oracle/_ref/dot_ref missing or failed: %s" % (r or {}).get("error", "not built")})
             return 0
@@ -167,181 +345,109 @@ def main():
                 "warmup": a.warmup, "ms_per_step": 1e3 * r["sec_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "reference",
-                                 "sample": "frames %d..%d of the same run, unmodified reference (OpenMP shim for TBB, CHOLMOD 3.0.12, OpenBLAS 1 thread/solver)" % (a.warmup + 1, a.warmup + a.steps),
+                                 "sample": "frames %d..%d of the same workload from rest (each step = one frame; bounded sample of the %d requested "
+                                           "frames: %.0f s of CPU work incl. %.0f s set-up); unmodified reference (OpenMP shim for TBB, CHOLMOD 3.0.12, "
+                                           "OpenBLAS 1 thread/solver)" % (w + 1, w + k, a.steps, r["wall_sec"], r["setup_sec"]),
                                  "inner_iters": r["inner_iters"], "timers_sec": r["timers_sec"]},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         _emit(line)
         return 0
 
-    import torch
-    import dot_b200 as D
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def fresh_nccl_id():
-        """Every communicator needs its own ncclUniqueId: rank 0 creates one, torch.distributed broadcasts the 128 bytes."""
-        if world == 1:
-            return None
-        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(D.nccl_unique_id()), dtype=torch.uint8))
-        torch.distributed.broadcast(buf, 0)
-        return bytes(buf.cpu().numpy().tobytes())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            torch.distributed.barrier()
-            torch.cuda.synchronize()
-
-    anim = D.Anim(wl["anim"], wl["V"])
-    fm = anim.fixed_mask()
-    fixed_idx = np.nonzero(fm)[0].astype(np.int32)
-
-    def make():
-        return D.Stepper(wl["V"], wl["T"], wl["epart"], fm, energy=wl["energy"], k=wl["k"], dt=DT, device=local_rank, rank=rank, world=world,
-                         nccl_id=fresh_nccl_id(), newton=wl["newton"])
-
-    # ---------------- value: resident positions ----------------
-    t_setup = time.time()
-    stp = make()
-    t_setup = time.time() - t_setup
-    an = D.Anim(wl["anim"], wl["V"])
-    x = wl["V"].copy()
-    iters = halv = 0
-    for f in range(a.warmup):
-        an.step(x, DT)
-        st = stp.frame_resident(fixed_idx, x[fixed_idx])
-        xs = stp.get_state()[0]
-        x[:] = xs
-    sampler = ClockSampler(local_rank)
+    ctx = Ctx()
+    sampler = ClockSampler(ctx.local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    l0 = stp.launch_count()
-    t0 = time.perf_counter()
-    dev_ms = solve_ms = refresh_ms = pc_ms = 0.0
-    pc_calls = 0
-    conv = True
-    for f in range(a.steps):
-        # the scripted handle motion only needs the handle rows, which the solve leaves where the script put them
-        an.step(x, DT)
-        st = stp.frame_resident(fixed_idx, x[fixed_idx])
-        iters += st.iters
-        halv += st.halvings
-        dev_ms += st.ms_total
-        solve_ms += st.ms_solve
-        refresh_ms += st.ms_refresh
-        pc_ms += st.ms_precond
-        pc_calls += st.precond_calls
-        conv = conv and bool(st.converged)
-    barrier()
-    t_value = time.perf_counter() - t0
-    launches = stp.launch_count() - l0
-    if world > 1:
-        tt = torch.tensor([t_value, dev_ms, pc_ms], dtype=torch.float64, device="cuda")
-        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        t_value, dev_ms, pc_ms = float(tt[0]), float(tt[1]), float(tt[2])
-    x_final = stp.get_state()[0]
-
-    # ---------------- per-kernel device times on the final state (CUDA events on the stepper's stream) ----------------
-    names = ["energy", "gradient", "elem_hessians", "fill", "factorize", "precondition", "dot"]
-    kms = {n: stp.time_kernels(i, 1 if a.profile_mode else 20) for i, n in enumerate(names)}
-    infos = [stp.solver_info(s) for s in range(wl["k"]) if s % world == rank]
-    nnz_l = sum(i.nnz_l for i in infos)
-    n_sub = sum(i.n for i in infos)
-    flops = sum(i.flops for i in infos)
+    R = gpu_frames(ctx, wl, a.steps, a.warmup, a.profile_mode)
+    sampler.stop_flag = True
+    kms = R["kms"]
+    names = list(kms)
     hbm, peak_src = peaks()
-    r = nV / nT
-    bytes_per = {"energy": 117.0 * nT, "gradient": 129.0 * nT, "elem_hessians": 1432.0 * nT, "precondition": 16.0 * nnz_l + 16.0 * n_sub}
+    bytes_per = {"energy": 117.0 * nT, "gradient": 129.0 * nT, "elem_hessians": 1000.0 * nT,
+                 "precondition": 16.0 * R["nnz_l"] + 16.0 * R["n_sub"]}
     kernels = {}
     for n in names:
         kernels[n] = {"ms": kms[n]}
         if n in bytes_per:
             gbs = bytes_per[n] / (kms[n] * 1e-3) / 1e9
             kernels[n].update({"algorithmic_bytes": bytes_per[n], "GB/s": gbs, "frac_hbm": gbs / hbm})
-    kernels["factorize"].update({"flops": flops, "GFLOP/s": flops / (kms["factorize"] * 1e-3) / 1e9})
-    del stp
+    kernels["elem_hessians"]["note"] = "bytes moved by this layout: 280 B read + 720 B written per tet (10 unique 3x3 blocks); the reference's 12x12 layout would be 1432 B/tet"
+    kernels["factorize"].update({"flops": R["flops"], "GFLOP/s": R["flops"] / (kms["factorize"] * 1e-3) / 1e9})
 
-    # ---------------- e2e: host positions in / out every frame through dotgpu_stepper_frame ----------------
-    stp = make()
-    an = D.Anim(wl["anim"], wl["V"])
-    x = wl["V"].copy()
-    pinned = torch.empty((nV, 3), dtype=torch.float64).pin_memory()
-    xe = pinned.numpy()
-    xe[:] = x
-    for f in range(a.warmup):
-        an.step(xe, DT)
-        stp.frame(xe)
-    barrier()
-    t0 = time.perf_counter()
-    e_iters = 0
-    for f in range(a.steps):
-        an.step(xe, DT)
-        st = stp.frame(xe)
-        e_iters += st.iters
-    loss = float(st.E)          # device->host read of the step's result (energy) is part of frame()
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        t_e2e = float(tt[0])
-    same = float(np.abs(xe - x_final).max())
-    sampler.stop_flag = True
-    del stp
+    # secondary record: config C2 on the reference's own mesh, same code path, short
+    secondary = None
+    if not a.no_secondary and a.workload != "bar17K" and not a.profile_mode:
+        wl2 = load_workload("bar17K")
+        R2 = gpu_frames(ctx, wl2, a.steps, a.warmup, with_kernels=False)
+        secondary = {"config": workload_config("bar17K", wl2, a.steps, a.warmup, world), "value": a.steps / R2["t_value"], "unit": "frames/s",
+                     "e2e": a.steps / R2["t_e2e"], "ms_per_step": 1e3 * R2["t_value"] / a.steps, "inner_iters": R2["iters"],
+                     "line_search_halvings": R2["halv"], "all_frames_converged": R2["conv"],
+                     "k5_ms_per_application": R2["pc_ms"] / max(R2["pc_calls"], 1),
+                     "k5_frac_hbm": (16.0 * R2["nnz_l"] + 16.0 * R2["n_sub"]) / (R2["pc_ms"] / max(R2["pc_calls"], 1) * 1e-3) / 1e9 / hbm,
+                     "solve_ms_per_step": R2["solve_ms"] / a.steps, "refresh_ms_per_step": R2["refresh_ms"] / a.steps}
+        if not a.no_parity:
+            secondary["parity"] = parity_run(ctx, wl2, 3, 1e-9)
+    parity = None
+    if not a.no_parity and not a.profile_mode and world == 1:
+        parity = parity_run(ctx, wl, 1 if nT > 300000 else 3, 1e-9)
 
     if rank != 0:
+        if world > 1:
+            ctx.torch.distributed.destroy_process_group()
         return 0
     cpu = None
-    if not a.no_cpu_baseline and world == 1:
-        r_cpu = run_reference(wl, a.cpu_frames, 0)
+    if not a.no_cpu_baseline and world == 1 and not a.profile_mode:
+        frames = a.cpu_frames or CPU_FRAME_CAP.get(a.workload, (0, 24))[1]
+        r_cpu = run_reference(wl, frames, 0)
         if r_cpu and "error" not in r_cpu:
             one = None
-            try:  # scaling context (SURVEY 8(d)): the same reference on ONE host thread, short sample
-                r1 = run_reference(wl, max(2, a.cpu_frames // 6), 0, threads=1)
-                if r1 and "error" not in r1:
-                    one = {"value": r1["fps"], "frames": r1["frames"], "inner_iters": r1["inner_iters"]}
-            except Exception:
-                one = None
+            if nT < 300000:
+                try:  # scaling context: the same reference on ONE host thread, short sample
+                    r1 = run_reference(wl, max(2, frames // 6), 0, threads=1)
+                    if r1 and "error" not in r1:
+                        one = {"value": r1["fps"], "frames": r1["frames"], "inner_iters": r1["inner_iters"]}
+                except Exception:
+                    one = None
             cpu = {"value": r_cpu["fps"], "unit": "frames/s", "cores": r_cpu["cores"], "kind": "reference", "one_thread": one,
                    "sample": "first %d frames of the same workload from rest (%.1f s of CPU work incl. %.1f s set-up); unmodified reference, OpenMP shim "
                              "for TBB, CHOLMOD 3.0.12 + OpenBLAS (1 thread per solver)" % (r_cpu["frames"], r_cpu["wall_sec"], r_cpu["setup_sec"]),
-                   "inner_iters": r_cpu["inner_iters"], "ms_per_iter": 1e3 * r_cpu["frames"] / r_cpu["fps"] / max(r_cpu["inner_iters"], 1)}
+                   "inner_iters": r_cpu["inner_iters"], "ms_per_iter": 1e3 * r_cpu["frames"] / r_cpu["fps"] / max(r_cpu["inner_iters"], 1),
+                   "timers_sec": r_cpu["timers_sec"]}
     # roofline of the dominant kernel group (K5): algorithmic bytes per application = 2 sweeps x 8 B x nnz(L) + 2 x 8 B x n
     # (SURVEY.md 8(d)); duration = the average over the preconditioner applications INSIDE the timed frames (CUDA events on
     # the stepper's stream, recorded around every application), not a separate micro-benchmark.
     k5_bytes = bytes_per["precondition"]
-    k5_ms = pc_ms / max(pc_calls, 1)
+    k5_ms = R["pc_ms"] / max(R["pc_calls"], 1)
     k5_gbs = k5_bytes / (k5_ms * 1e-3) / 1e9 if k5_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(a.workload, {}).get("k_solve_stream_dram_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "K5 k_solve_stream: all per-subdomain supernodal triangular solves of one preconditioner application "
-                                      "(forward + backward) as one persistent TMA-streamed dataflow kernel (+ the fused gather; the scatter/average kernel is included in the timed span)",
+        traffic = json.load(open(tp)).get(a.workload, {}).get("k_solve_dram_bytes_per_launch")
+    roof = {"bound": "hbm", "kernel": "K5 k_solve_tasks: all per-subdomain supernodal triangular solves of one preconditioner application "
+                                      "(forward + backward) as one persistent TMA-streamed task-graph kernel (+ the fused gather; the scatter/average kernel is "
+                                      "included in the timed span); rank 0's share at N > 1",
             "achieved": k5_gbs, "peak": hbm, "unit": "GB/s", "frac": k5_gbs / hbm, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": k5_bytes, "avg_launch_ms_in_timed_region": k5_ms, "launches_in_timed_region": pc_calls,
-            "share_of_frame": pc_ms / max(dev_ms, 1e-9), "isolated_ms": kms["precondition"]}
-    line = {"metric": "simulated frames/sec (Newton-converged)", "value": a.steps / t_value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "algorithmic_bytes_per_launch": k5_bytes, "avg_launch_ms_in_timed_region": k5_ms, "launches_in_timed_region": R["pc_calls"],
+            "share_of_frame": R["pc_ms"] / max(R["dev_ms"], 1e-9), "isolated_ms": kms["precondition"]}
+    line = {"metric": "simulated frames/sec (Newton-converged)", "value": a.steps / R["t_value"], "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * R["t_value"] / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
-            "e2e": {"value": a.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 24 * nV, "d2h_bytes_per_step": 24 * nV + 8,
-                    "max_abs_diff_vs_resident_run": same},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
+            "e2e": {"value": a.steps / R["t_e2e"], "unit": "frames/s", "h2d_bytes_per_step": 24 * nV, "d2h_bytes_per_step": 24 * nV + 8,
+                    "max_abs_diff_vs_resident_run": R["e2e_vs_resident"]},
+            "gpu_launches": R["launches"], "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
             "assembly_tets_per_s": {"energy+gradient": nT / ((kms["energy"] + kms["gradient"]) * 1e-3),
                                     "hessian+fill": nT / ((kms["elem_hessians"] + kms["fill"]) * 1e-3)},
-            "inner_iters": iters, "line_search_halvings": halv, "all_frames_converged": conv, "device_ms_per_step": dev_ms / a.steps,
-            "solve_ms_per_step": solve_ms / a.steps, "refresh_ms_per_step": refresh_ms / a.steps, "setup_sec": t_setup,
-            "nnz_L": nnz_l, "factor_flops": flops}
+            "inner_iters": R["iters"], "line_search_halvings": R["halv"], "all_frames_converged": R["conv"], "device_ms_per_step": R["dev_ms"] / a.steps,
+            "solve_ms_per_step": R["solve_ms"] / a.steps, "refresh_ms_per_step": R["refresh_ms"] / a.steps, "setup_sec": R["setup_sec"],
+            "nnz_L": R["nnz_l"], "factor_flops": R["flops"], "owned_subdomains_rank0": R["owned_subdomains"]}
+    if parity is not None:
+        line["parity"] = parity
+    if secondary is not None:
+        line["secondary"] = secondary
     if cpu:
         line["cpu_baseline"] = cpu
     _emit(line)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        ctx.torch.distributed.destroy_process_group()
     return 0
 
 

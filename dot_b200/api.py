@@ -41,7 +41,7 @@ class FrameStats(C.Structure):
     _fields_ = [("iters", C.c_int32), ("halvings", C.c_int32), ("energy_evals", C.c_int32), ("converged", C.c_int32),
                 ("E", C.c_double), ("grad_sqnorm", C.c_double), ("target", C.c_double), ("ms_total", C.c_double),
                 ("ms_solve", C.c_double), ("ms_refresh", C.c_double), ("ms_precond", C.c_double), ("precond_calls", C.c_int32),
-                ("pad_", C.c_int32)]
+                ("line_search_failed", C.c_int32)]
 
 
 def lib():
@@ -104,6 +104,14 @@ def owned_subdomains(k, rank, world):
     out = np.empty(n, dtype=np.int32)
     lib().dotgpu_owned_subdomains(int(k), int(rank), int(world), _p(out))
     return out
+
+
+def partition(nV, tets, k):
+    """METIS<3>::partMesh with the reference's vendored METIS and option vector: element labels [nT] int32 (bit-exact)."""
+    T = _i32(tets)
+    ep = np.empty(T.shape[0], dtype=np.int32)
+    _chk(lib().dotgpu_partition(int(nV), T.shape[0], _p(T), int(k), _p(ep)))
+    return ep
 
 
 def mesh_features(V_rest, tets, YM=1e5, PR=0.4, rho=1000.0):
@@ -406,6 +414,13 @@ class Stepper:
 
     def launch_count(self):
         return int(lib().dotgpu_stepper_launch_count(self.h))
+
+    def owned(self):
+        """Subdomain ids this rank factors and solves."""
+        n = lib().dotgpu_stepper_get_owned(self.h, None)
+        out = np.empty(max(n, 0), dtype=np.int32)
+        lib().dotgpu_stepper_get_owned(self.h, _p(out))
+        return [int(v) for v in out]
 
     def solver_info(self, sub):
         i = SolverInfo()

@@ -586,6 +586,17 @@ int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* 
     *ms_out = s->s.time_kernels(which, reps);
     API_END
 }
+int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out) {
+    if (!s) return DOTGPU_ERR_INVALID;
+    if (out)
+        for (size_t i = 0; i < s->s.owned.size(); ++i) out[i] = s->s.owned[i];
+    return (int)s->s.owned.size();
+}
+int dotgpu_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out) {
+    API_BEGIN
+    metis_partition(nV, nT, tets, k, epart_out);
+    API_END
+}
 int64_t dotgpu_stepper_launch_count(dotgpu_stepper* s) { return s ? g_launch_count - s->s.launches0 : 0; }
 int dotgpu_stepper_get_solver_info(dotgpu_stepper* s, int sub, dotgpu_solver_info* info) {
     API_BEGIN

@@ -27,7 +27,7 @@ struct DeviceMesh {
     DevBuf<double> epart;   // elastic energy partial per K2 CTA (energy fused into the gradient pass)
     DevBuf<double> He;      // 90*nT, allocated on first use
     DevBuf<double> partial; // block partial sums for reductions
-    int n_partial = 0;
+    int n_partial = 0, nsm = 148;
     DevBuf<unsigned> counter;  // last-block detection of the fused energy reduction (self-resetting)
 
     void init(int energy_type, int nV_, int nT_, const int32_t* tets_h, const double* DmInv_rowmajor, const double* vol_h,

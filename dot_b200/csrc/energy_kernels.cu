@@ -435,7 +435,15 @@ void DeviceMesh::init(int energy_type, int nV_, int nT_, const int32_t* tets_h, 
         vp_idx.upload(vidx, st);
         gpart.alloc(3 * (size_t)std::max(npart, 1));
     }
-    n_partial = 148 * 8 + 8;
+    {   // reduction grids are sized from the SM count of the device this mesh lives on
+        int dev = 0;
+        DG_CUDA(cudaGetDevice(&dev));
+        DG_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        // the opt-in shared-memory limit is per device and per function: set it for the device of this mesh
+        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_FCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
+        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_SNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
+    }
+    n_partial = nsm * 8 + 8;
     partial.alloc(n_partial);
     counter.alloc(1);
     counter.zero(st);
@@ -466,14 +474,14 @@ void DeviceMesh::set_fixed(const unsigned char* fixed_h, cudaStream_t st) {
     } while (0)
 
 void launch_energy(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* E_out, cudaStream_t st) {
-    // at most 6 tet CTAs + 1 inertia CTA of 256 threads per SM (148 SMs): <= 1036 partials for the last block
-    const int nbT = std::min(ceil_div(m.nT, ETPB), 148 * 6), nbV = xTilde ? std::min(ceil_div(m.nV, ETPB), 148) : 0;
+    // at most 6 tet CTAs + 1 inertia CTA of 256 threads per SM: <= 7 * #SM partials for the last block
+    const int nbT = std::min(ceil_div(m.nT, ETPB), m.nsm * 6), nbV = xTilde ? std::min(ceil_div(m.nV, ETPB), m.nsm) : 0;
     DISPATCH_EN(m, k_energy, nbT + nbV, ETPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, xTilde,
                 m.mass.p, coef, m.partial.p, m.counter.p, E_out, (double*)nullptr);
 }
 
 void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStream_t st) {
-    const int nbT = std::min(ceil_div(m.nT, ETPB), 148 * 6);
+    const int nbT = std::min(ceil_div(m.nT, ETPB), m.nsm * 6);
     DISPATCH_EN(m, k_energy, nbT, ETPB, st, m.nT, m.nV, nbT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x,
                 (const double*)nullptr, (const double*)nullptr, 1.0, (double*)nullptr, (unsigned*)nullptr, (double*)nullptr, out);
 }
@@ -507,12 +515,6 @@ void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S,
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st) {
     if (m.He.n < (size_t)HE_DBL * m.nT) m.He.alloc((size_t)HE_DBL * m.nT);
     int nb = ceil_div(m.nT, TPB);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_FCR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
-        DG_CUDA(cudaFuncSetAttribute(k_hessian<DG_SNH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * HE_LD * (int)sizeof(double)));
-        attr_set = true;
-    }
     DISPATCH_EN_SMEM(m, k_hessian, nb, TPB, TPB * HE_LD * sizeof(double), st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef,
                 project ? 1 : 0, m.He.p);
 }

@@ -64,4 +64,7 @@ struct DDHost {
                const double* V_rest, double rho, const double* mass_global, bool with_fill, const std::vector<char>* sub_mask = nullptr);
 };
 
+// a14: element labels from the reference's vendored METIS (partition_host.cpp; dlopen of libdotmetis.so)
+void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out);
+
 }  // namespace dotgpu

@@ -88,10 +88,15 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     nV = nV_;
     nT = nT_;
     DG_REQUIRE(nV > 0 && nT > 0 && Vr && T && ep, "null or empty mesh");
-    DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= 8, "bad subdomain count / history size");
+    // history + 1 (S, Y) buffers are in use (the candidate pair lives in a spare slot), and the device scalar table has
+    // LB_MAXH slots per row (linalg.h) -> at most LB_MAXH - 1 pairs
+    static_assert(SC_YP - SC_SG == LB_MAXH && SC_XI - SC_YP == LB_MAXH && SC_SY - SC_XI == LB_MAXH && SC_COUNT == SC_SY + LB_MAXH * LB_MAXH,
+                  "scalar table layout assumes LB_MAXH slots");
+    DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= LB_MAXH - 1, "bad subdomain count / history size (max 7 pairs)");
     DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
     DG_REQUIRE(cfg.dt > 0, "dt must be positive");
     newton = (cfg.flags & DOTGPU_FLAG_NEWTON) != 0;
+    if (const char* e = std::getenv("DOTGPU_DEBUG_ASCENT")) debug_ascent = *e == '1';
     if (newton) {
         DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
         cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
@@ -333,7 +338,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     double E = h_sc[SC_E], gg = h_sc[SC_GG];
     iter_log.insert(iter_log.end(), {0.0, E, gg});
     int iters = 0;
-    bool sg_valid = false;
+    bool sg_valid = false, stopped = false;
     std::vector<int> free_slots;
     for (int i = 0; i <= cfg.history; ++i) free_slots.push_back(i);
     do {
@@ -366,6 +371,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
             if (!fused) launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
         launch_lbfgs_p(n, p.p, H, sc.p, st);
+        if (debug_ascent) launch_negate(n, p.p, sc.p + SC_PG, st);  // tests only (DOTGPU_DEBUG_ASCENT=1): forces the line search to fail
         // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
         const double* alpha_dev = newton ? nullptr : sc.p + SC_ALPHA;  // Newton: initStepSize = 1 (Optimizer.cpp:1088)
         if (!newton) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
@@ -386,7 +392,10 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
             while (true) {
                 alpha /= 2.0;
                 ++halvings;
-                if (alpha == 0.0) break;
+                if (alpha == 0.0) {  // Optimizer.cpp:816-824: the step underflowed, the line search has failed
+                    stopped = true;
+                    break;
+                }
                 launch_axpy_dev(n, x.p, x0.p, p.p, nullptr, alpha, st);
                 Et = energy_at(x.p);
                 ++evals;
@@ -409,12 +418,15 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                 hist.pop_front();
             }
         }
+        // a failed line search ends the time step at once, uncounted and without the Hessian refresh
+        // (DOTTimeStepper.cpp:313-317 returns before innerIterAmt++ and before updateHessianAndFactor)
+        if (stopped) break;
         ++iters;
         iter_log.insert(iter_log.end(), {alpha, E, gg});
     } while (gg > target && iters < cfg.max_iters);
     DG_CUDA(cudaEventRecord(ev[1], st));
     // ---- Hessian refresh at the end of the step (DOTTimeStepper.cpp:343, 349-380); Newton refactorises per iteration instead ----
-    if (!newton) refresh();
+    if (!newton && !stopped) refresh();
     DG_CUDA(cudaEventRecord(ev[2], st));
     // ---- BE update (Optimizer.cpp:354-361) ----
     launch_velocity(nV, vel.p, x.p, xn.p, dt, st);
@@ -429,7 +441,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         stats->iters = iters;
         stats->halvings = halvings;
         stats->energy_evals = evals;
-        stats->converged = gg <= target;
+        stats->converged = !stopped && gg <= target;
         stats->E = E;
         stats->grad_sqnorm = gg;
         stats->target = target;
@@ -448,7 +460,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         }
         stats->ms_precond = pc;
         stats->precond_calls = iters;
-        stats->pad_ = 0;
+        stats->line_search_failed = stopped ? 1 : 0;
     }
 }
 

@@ -108,3 +108,10 @@ def write_script(path: str, msh_path: str, energy: str = "SNH", parts: int = 8, 
 def preset(name: str):
     nx, ny, nz = PRESETS[name]
     return kuhn_bar(nx, ny, nz)
+
+
+def load_mesh_npz(path: str):
+    """(V [nV,3] float64 as parsed from the .msh, T [nT,4] int32) of a mesh fixture written by oracle/gen_golden.py --meshes
+    (the reference's own input/tetMeshes/*.msh, e.g. bar17K, bunny5K, horse38K)."""
+    z = np.load(path)
+    return np.ascontiguousarray(z["V"], dtype=np.float64), np.ascontiguousarray(z["T"], dtype=np.int32)

@@ -128,6 +128,11 @@ int dotgpu_solver_get_symbolic(dotgpu_solver* s, int32_t* perm, int32_t* super_p
  * and are an INPUT here (bit-exact labels require the vendored METIS).
  * ------------------------------------------------------------------------------------------ */
 typedef struct dotgpu_dd dotgpu_dd;
+/* METIS<3>::partMesh (Utils/METIS.hpp:109-160, options :265-321; called at ADMMDDTimeStepper.cpp:88-92): k-way partition of the
+ * dual graph (ncommon = 3) with the reference's vendored METIS 5.1.0 (libdotmetis.so, built by dot_b200/build.py from the sources
+ * under the reference tree; 64-bit idx_t, 32-bit real_t).  epart_out [nT] = subdomain label per tet, bit-exact with the reference's.
+ * Returns DOTGPU_ERR_STATE when libdotmetis.so is not available (then pass labels produced elsewhere to the calls below). */
+int dotgpu_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out);
 int dotgpu_dd_create(dotgpu_dd** out, int nV, int nT, const int32_t* tets, const int32_t* epart, int k,
                      const uint8_t* fixed_mask);
 void dotgpu_dd_destroy(dotgpu_dd* d);
@@ -192,7 +197,8 @@ typedef struct dotgpu_frame_stats {
     double E, grad_sqnorm, target;
     double ms_total, ms_solve, ms_refresh;  /* device times (CUDA events) */
     double ms_precond;        /* device time of the preconditioner applications (K5) of this frame, CUDA events on the stepper's stream */
-    int32_t precond_calls, pad_;
+    int32_t precond_calls;
+    int32_t line_search_failed; /* 1 if the step length halved to 0 (Optimizer.cpp:816-824): the time step ended there, converged = 0 */
 } dotgpu_frame_stats;
 
 /* Builds everything precompute() builds: mesh features, DD from labels, patterns, symbolic analysis of
@@ -230,6 +236,8 @@ int dotgpu_stepper_set_rel_tol(dotgpu_stepper* s, double rel_tol);
  * refreshes (K3+K4+factor) / preconditioner applications (K5) on resident data, return avg ms by CUDA events */
 int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* ms_out);
 int64_t dotgpu_stepper_launch_count(dotgpu_stepper* s); /* kernels launched by this handle so far */
+/* the subdomains this rank factors and solves (ascending; balanced by nnz(L) over the ranks); returns their number */
+int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out);
 int dotgpu_stepper_get_solver_info(dotgpu_stepper* s, int sub, dotgpu_solver_info* info);
 
 #ifdef __cplusplus

@@ -41,6 +41,15 @@ CASES = [
     ("small_fcr_k3_stretch", "bar_small", "FCR", 3, "stretch", 5, [5], 48, 0.025),
     ("small_snh_k5_tsns_dt24", "bar_small", "SNH", 5, "twistnsns_old", 8, [8], 16, 0.0416667),
 ]
+# back-tracking cases: a large time step makes the reference's line search halve (21 resp. 92 halvings in these runs,
+# Optimizer.cpp:803-833); iterStats.txt is written with 17 significant digits (--full-precision)
+HALVING_CASES = [
+    ("small_snh_k4_twist_dt200", "bar_small", "SNH", 4, "twist", 6, [1, 6], 16, 0.2),
+    ("small_fcr_k3_tsns_dt200", "bar_small", "FCR", 3, "twistnsns", 8, [1, 8], 16, 0.2),
+]
+# the reference's own input meshes (BASELINE.json configs C1, C2, C5): nodes / tets as parsed from input/tetMeshes/*.msh
+# plus the METIS labels of the reference's wrapper for the subdomain counts the configs name
+MESH_CASES = [("bunny5K", [6]), ("bar17K", [8]), ("horse38K", [16])]
 # Projected Newton (`timeStepper Newton`, Optimizer::solve_oneStep - the reference's "1 subdomain" case): same tuple, parts unused
 PN_CASES = [
     ("small_fcr_newton_twist", "bar_small", "FCR", 4, "twist", 4, [1, 4], 16, 0.025),
@@ -78,7 +87,7 @@ def make_mesh(tmp, preset):
     return V, T, msh
 
 
-def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepper="DOT"):
+def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepper="DOT", full_precision=False):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
         V, T, msh = make_mesh(tmp, preset)
@@ -89,6 +98,8 @@ def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepp
                 "--dump-frames", ",".join(map(str, dumps)), "--he-cap", str(he_cap)]
         if stepper != "DOT":
             args += ["--stepper", stepper]
+        if full_precision:
+            args += ["--full-precision"]
         stats = run_ref(args, tmp)
         arrs = collect(dd)
         arrs["iterStats"] = np.array(open(os.path.join(dd, "iterStats.txt")).read())
@@ -123,6 +134,30 @@ def gen_kernel_case(name, preset, energy, parts, amp, seed):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def gen_mesh(name, parts_list):
+    """tests/golden/mesh_<name>.npz = the reference's input/tetMeshes/<name>.msh as arrays (V float64 exactly as parsed,
+    T int32 0-based) and labels_<name>_k<k>.npz from the reference's METIS wrapper on that mesh."""
+    from dot_b200 import io as dio
+    ref_root = os.environ.get("DOT_REFERENCE", "/root/reference")
+    msh = os.path.join(ref_root, "input", "tetMeshes", name + ".msh")
+    V, T, SF = dio.read_msh(msh)
+    np.savez_compressed(os.path.join(GOLD, "mesh_%s.npz" % name), V=V, T=T.astype(np.int32))
+    print("mesh", name, V.shape, T.shape)
+    for parts in parts_list:
+        tmp = tempfile.mkdtemp(prefix="golden_")
+        try:
+            script = os.path.join(tmp, "s.txt")
+            meshgen.write_script(script, msh, energy="SNH", parts=parts, anim="twist")
+            dd = os.path.join(tmp, "dump")
+            run_ref(["--script", script, "--frames", "0", "--quiet", "--dump-dir", dd, "--labels-only"], tmp)
+            ep = np.load(os.path.join(dd, "setup", "epart.npy"))
+            assert ep.min() >= 0 and ep.max() == parts - 1
+            np.savez_compressed(os.path.join(GOLD, "labels_%s_k%d.npz" % (name, parts)), epart=ep.astype(np.uint8))
+            print("labels", name, parts, np.bincount(ep).tolist()[:8], "...")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
 def gen_labels(preset, parts):
     """Labels only: run set-up (METIS + DD) and keep epart."""
     tmp = tempfile.mkdtemp(prefix="golden_")
@@ -144,6 +179,7 @@ def gen_labels(preset, parts):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--labels", action="store_true")
+    ap.add_argument("--meshes", action="store_true", help="fixtures of the reference's own input meshes + their METIS labels")
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -152,12 +188,19 @@ if __name__ == "__main__":
     for c in CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c)
+    for c in HALVING_CASES:
+        if not a.only or a.only in c[0]:
+            gen_case(*c, full_precision=True)
     for c in PN_CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c, stepper="Newton")
     for c in KERNEL_CASES:
         if not a.only or a.only in c[0]:
             gen_kernel_case(*c)
+    if a.meshes:
+        for c in MESH_CASES:
+            if not a.only or a.only in c[0]:
+                gen_mesh(*c)
     if a.labels:
         for c in LABEL_CASES:
             if not a.only or a.only in c[0]:

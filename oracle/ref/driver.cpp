@@ -292,12 +292,14 @@ static void usage()
 {
     std::cerr << "dot_ref --script <file.txt> [--mesh <file.msh>] [--energy SNH|FCR] [--parts K] [--stepper DOT|Newton]\n"
                  "        [--tol T] [--dt DT] [--anim <script name>] [--frames N] [--threads N] [--quiet] [--labels-only]\n"
-                 "        [--dump-dir D] [--dump-frames a,b,c] [--he-cap N] [--kernel-state V.npy] [--stats-json file]\n";
+                 "        [--dump-dir D] [--dump-frames a,b,c] [--he-cap N] [--kernel-state V.npy] [--stats-json file]\n"
+                 "        [--final-V V.npy] [--full-precision]\n";
 }
 
 int main(int argc, char** argv)
 {
-    std::string script, meshOverride, energy, stepper, anim, dumpDir, kernelState, statsJson;
+    std::string script, meshOverride, energy, stepper, anim, dumpDir, kernelState, statsJson, finalV;
+    bool fullPrecision = false;
     int parts = -1, frames = 10, threads = 0;
     long heCap = -1;
     double tol = -1, dtOverride = -1;
@@ -323,6 +325,8 @@ int main(int argc, char** argv)
         else if (a == "--he-cap") heCap = std::stol(next());
         else if (a == "--kernel-state") kernelState = next();
         else if (a == "--stats-json") statsJson = next();
+        else if (a == "--final-V") finalV = next();            // positions after the last frame, [nV,3] float64 .npy
+        else if (a == "--full-precision") fullPrecision = true;  // iterStats.txt with 17 significant digits (default: the reference's 6)
         else if (a == "--dump-frames") { std::stringstream ss(next()); std::string t; while (std::getline(ss, t, ',')) dumpFrames.insert(std::stoi(t)); }
         else { usage(); return 2; }
     }
@@ -456,6 +460,7 @@ int main(int argc, char** argv)
         return 0;
     }
 
+    if (fullPrecision) opt->file_iterStats.precision(17);
     // ---- frame loop: main.cpp:92-132 ----
     std::vector<double> frameSec;
     std::vector<int> frameIters;
@@ -482,6 +487,11 @@ int main(int argc, char** argv)
     }
     const DOT::Mesh<DIM>& R = opt->getResult();
     double sumV = R.V.sum(), sqV = R.V.squaredNorm();
+    if (!finalV.empty()) {
+        std::vector<double> rm((size_t)R.V.rows() * 3);
+        for (long v = 0; v < R.V.rows(); ++v) for (int c = 0; c < 3; ++c) rm[v * 3 + c] = R.V(v, c);
+        npy_f64(finalV, {(long)R.V.rows(), 3}, rm.data());
+    }
     std::ostringstream js;
     js.precision(17);
     js << "{\"frames\": " << frames << ", \"inner_iters\": " << opt->getInnerIterAmt() << ", \"loop_sec\": " << loopSec

@@ -493,3 +493,140 @@ def test_edge_cases_tiny_meshes_and_error_codes():
     Tb[0, [1, 2]] = Tb[0, [2, 1]]
     with pytest.raises(D.DotGpuError):
         D.Stepper(Vb, Tb, np.zeros(Tb.shape[0], dtype=np.int32), np.zeros(Vb.shape[0], dtype=np.uint8), energy="SNH", k=1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: back-tracking branch, history limits, line-search failure, the reference's own meshes at full size
+HALVING_CASES = {"small_snh_k4_twist_dt200": (1e-7, 1e-8, 1e-5, 1e-8), "small_fcr_k3_tsns_dt200": (5e-3, 1e-4, 1e-2, 1e-6)}
+
+
+@pytest.mark.parametrize("name", sorted(HALVING_CASES))
+def test_stepper_follows_reference_through_line_search_halvings(name):
+    """a13, the halving branch (Optimizer.cpp:803-833; stepper.cu back-tracking loop): dt = 0.2 makes the reference halve
+    its step 21 (SNH) / 92 (FCR) times in these runs.  From the reference's state after frame 1 the device stepper follows
+    the reference's 17-digit iterStats iteration by iteration: same iteration counts, step sizes (incl. every halved one),
+    energies, |g|^2, final positions.  Tolerances per case as measured for the CPU oracle on the same fixtures
+    (tests/test_oracle_golden.py): the FCR path amplifies the ~1e-10 noise of the reference's own AVX SVD."""
+    g = Golden(name)
+    ta, te, tg, tx = HALVING_CASES[name]
+    stp, anim = _stepper(g)
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    x = g["setup/V_rest"].copy()
+    for _ in range(f0):
+        anim.step(x, g.meta["dt"])
+    stp.set_state(g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    x = g["frame%d/V" % f0].copy()
+    ref_stats = g.iter_stats()
+    halvings = 0
+    for f in range(f0 + 1, dumps[-1] + 1):
+        anim.step(x, g.meta["dt"])
+        fs = stp.frame(x)
+        ref = ref_stats[ref_stats[:, 0] == f - 1]
+        log = stp.iter_log()
+        assert fs.iters == g.meta["stats"]["frame_iters"][f - 1], f
+        assert fs.converged == 1 and fs.line_search_failed == 0
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=ta, atol=0), f
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=te), f
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=tg), f
+        halvings += fs.halvings
+    assert halvings > 0
+    # the reference's count covers frames 1..last; frame 1 is not replayed here
+    assert halvings <= g.meta["stats"]["line_search_halvings"]
+    assert np.abs(x - g["frame%d/V" % dumps[-1]]).max() < tx
+
+
+def test_history_limits_and_line_search_failure(monkeypatch):
+    """(1) history + 1 pair buffers share a scalar table with LB_MAXH = 8 slots per row: 7 pairs is the
+    maximum, 8 is rejected; a run with 7 pairs converges to the same minimiser as the default 5.
+    (2) a failed line search (step halved to 0, Optimizer.cpp:816-824) ends the time step: converged = 0,
+    line_search_failed = 1, no hang - forced here by searching along the reversed direction (DOTGPU_DEBUG_ASCENT)."""
+    g = Golden("small_snh_k4_twist")
+    V, T = g["setup/V_rest"], g["setup/F"]
+    a = D.Anim(g.meta["anim"], V)
+    with pytest.raises(D.DotGpuError):
+        D.Stepper(V, T, g["setup/epart"], a.fixed_mask(), energy="SNH", k=g.k, history=8)
+    xs = {}
+    for h in (5, 7, 1, 0):
+        a = D.Anim(g.meta["anim"], V)
+        stp = D.Stepper(V, T, g["setup/epart"], a.fixed_mask(), energy="SNH", k=g.k, history=h, rel_tol=1e-8)
+        x = V.copy()
+        for f in range(3):
+            a.step(x, g.meta["dt"])
+            fs = stp.frame(x)
+            assert fs.converged == 1, (h, f)
+        xs[h] = x
+    for h in (7, 1, 0):
+        assert np.abs(xs[h] - xs[5]).max() < 1e-6, h
+    monkeypatch.setenv("DOTGPU_DEBUG_ASCENT", "1")
+    a = D.Anim(g.meta["anim"], V)
+    stp = D.Stepper(V, T, g["setup/epart"], a.fixed_mask(), energy="SNH", k=g.k)
+    monkeypatch.delenv("DOTGPU_DEBUG_ASCENT")
+    x = V.copy()
+    a.step(x, g.meta["dt"])
+    fs = stp.frame(x)
+    assert fs.line_search_failed == 1 and fs.converged == 0 and fs.iters == 0
+    assert fs.halvings > 1000          # 0.1 / 2^h underflows after ~1071 halvings
+    assert np.isfinite(x).all()
+
+
+REAL_MESHES = [
+    # fixture, energy, k, script, dt, frames  (BASELINE.json configs C2, C1, C5)
+    ("bar17K", "SNH", 8, "twist", 0.025, 3),
+    ("bunny5K", "FCR", 6, "twistnsns", 0.025, 3),
+    ("horse38K", "SNH", 16, "twistnsns_old", 0.0416667, 2),
+]
+
+
+@pytest.mark.parametrize("mesh,energy,k,anim,dt,frames", REAL_MESHES)
+def test_full_size_position_parity_on_reference_meshes(tmp_path, mesh, energy, k, anim, dt, frames):
+    """The reference's own input meshes (fixtures tests/golden/mesh_*.npz + its METIS labels) at full size: the unmodified
+    reference binary (oracle/_ref/dot_ref) and the device stepper run the same script from rest with tol 1e-9 (SURVEY 8(c):
+    at a tight tolerance both converge to the same minimiser); positions after every run must agree to 1e-6 of the
+    bounding box (longest edge = 1 after the loader's normalisation), every frame converged."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "dot_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dot_ref not built")
+    Vraw, T = meshgen.load_mesh_npz(os.path.join(root, "tests", "golden", "mesh_%s.npz" % mesh))
+    ep = np.load(os.path.join(root, "tests", "golden", "labels_%s_k%d.npz" % (mesh, k)))["epart"].astype(np.int32)
+    tmp = str(tmp_path)
+    msh = os.path.join(tmp, "m.msh")
+    meshgen.write_msh(msh, Vraw, T)
+    script = os.path.join(tmp, "s.txt")
+    meshgen.write_script(script, msh, energy=energy, parts=k, anim=anim, dt=dt)
+    st, Vref = _run_ref_final(exe, tmp, script, frames, 1e-9)
+    V = meshgen.normalise_like_loader(Vraw)
+    a = D.Anim(anim, V)
+    stp = D.Stepper(V, T, ep, a.fixed_mask(), energy=energy, k=k, dt=dt, rel_tol=1e-9)
+    assert abs(stp.target - st["targetGRes"]) <= 1e-10 * stp.target
+    x = V.copy()
+    iters = 0
+    for f in range(frames):
+        a.step(x, dt)
+        fs = stp.frame(x)
+        assert fs.converged == 1, f
+        iters += fs.iters
+    err = float(np.abs(x - Vref).max())
+    assert err < 1e-6, (err, iters, st["inner_iters"])
+    # same amount of work as the reference (iteration paths differ in the last digits only)
+    assert abs(iters - st["inner_iters"]) <= 0.15 * st["inner_iters"] + 3, (iters, st["inner_iters"])
+
+
+def _run_ref_final(exe, tmp, script, frames, tol, threads=None):
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nthr = str(threads or os.cpu_count() or 4)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=nthr)
+    blas = os.path.join(root, "oracle", "_ref", "blasdir.txt")
+    if os.path.exists(blas):
+        env["LD_LIBRARY_PATH"] = open(blas).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
+    fv = os.path.join(tmp, "finalV.npy")
+    out = subprocess.run([exe, "--script", script, "--frames", str(frames), "--quiet", "--threads", nthr, "--tol", repr(tol), "--final-V", fv],
+                         cwd=tmp, env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    st = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    return st, np.load(fv)

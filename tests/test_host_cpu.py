@@ -190,3 +190,23 @@ def test_symbolic_on_global_pattern_is_sane():
     perm, L = _multifrontal_numpy(info.n, ia, ja, a, s.symbolic())
     A = O.csr_upper_to_full(ia, ja, a).toarray()
     assert rel(L @ L.T, A[np.ix_(perm, perm)]) < 1e-12
+
+
+@pytest.mark.parametrize("mesh,k", [("bar5K_like", 6), ("bar17K_like", 8), ("bunny5K", 6), ("bar17K", 8), ("horse38K", 16)])
+def test_partition_labels_bit_exact_with_reference_metis(mesh, k):
+    """a14: dotgpu_partition (the reference's vendored METIS 5.1.0 behind the C ABI, option vector of Utils/METIS.hpp:265-321)
+    reproduces the labels of the reference's own wrapper bit for bit - structured bars and the reference's input meshes."""
+    import os
+    from dot_b200 import meshgen
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if not os.path.exists(os.path.join(os.path.dirname(D.lib_path()), "libdotmetis.so")):
+        pytest.skip("libdotmetis.so not built (needs the reference's vendored METIS sources at build time)")
+    if mesh in meshgen.PRESETS:
+        V, T = meshgen.preset(mesh)
+    else:
+        V, T = meshgen.load_mesh_npz(os.path.join(gold, "mesh_%s.npz" % mesh))
+    ep = D.partition(V.shape[0], T, k)
+    ref = np.load(os.path.join(gold, "labels_%s_k%d.npz" % (mesh, k)))["epart"]
+    assert ep.dtype == np.int32 and np.array_equal(ep, ref)
+    with pytest.raises(D.DotGpuError):
+        D.partition(V.shape[0], T, 1)

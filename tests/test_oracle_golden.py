@@ -214,3 +214,37 @@ def test_projected_newton_follows_reference_from_restart(name):
         assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3)
         if g.has("frame%d/V" % f):
             assert np.abs(stp.x - g["frame%d/V" % f]).max() < 1e-8, f
+
+
+HALVING_CASES = ["small_snh_k4_twist_dt200", "small_fcr_k3_tsns_dt200"]
+# (alpha, E, |g|^2 relative, final |dx|): SNH has no SVD in E / g and follows to 1e-9; the FCR run amplifies the ~1e-10
+# noise of the reference's AVX SVD over 7 frames x ~30 iterations of a halving-heavy path (measured: alpha 7e-4 in the
+# worst frame, iteration counts identical in every frame, final positions 1e-8)
+HALVING_TOL = {"small_snh_k4_twist_dt200": (1e-7, 1e-8, 1e-5, 1e-8), "small_fcr_k3_tsns_dt200": (5e-3, 1e-4, 1e-2, 1e-6)}
+
+
+@pytest.mark.parametrize("name", HALVING_CASES)
+def test_time_stepping_follows_reference_through_line_search_halvings(name):
+    """Back-tracking parity (Optimizer.cpp:803-833): dt = 0.2 makes the reference halve its step in many iterations
+    (21 resp. 92 halvings in these runs).  Restart from the reference's state after frame 1 and follow it iteration by
+    iteration; these fixtures carry iterStats.txt with 17 digits, so step sizes / energies are compared tightly."""
+    g = Golden(name)
+    assert g.meta["stats"]["line_search_halvings"] > 0
+    m = mesh_of(g)
+    dumps = g.meta["dumps"]
+    stp = O.DOTStepper(m, g.meta["energy"], g["setup/epart"], g.meta["anim"], g.meta["dt"])
+    f0 = dumps[0]
+    stp.restart(f0, g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    for f in range(f0 + 1, dumps[-1] + 1):
+        stp.log = []
+        it = stp.step_frame()
+        ref = _frame_rows(g, f)
+        log = np.asarray(stp.log)
+        assert it == g.meta["stats"]["frame_iters"][f - 1], f
+        ta, te, tg, tx = HALVING_TOL[name]
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=ta, atol=0), f        # step sizes incl. the halved ones
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=te), f                # E
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=tg), f                # |g|^2
+    assert stp.halvings > 0    # the comparison above went through the halving branch
+    f = dumps[-1]
+    assert np.abs(stp.x - g["frame%d/V" % f]).max() < tx
