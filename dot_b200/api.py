@@ -22,7 +22,7 @@ class DotGpuError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libdotgpu.so")
+    return os.environ.get("DOTGPU_LIB") or os.path.join(_HERE, "libdotgpu.so")
 
 
 class SolverInfo(C.Structure):

@@ -16,7 +16,8 @@
 //   * 8 consumer warps wait for the data (mbarrier) and for the task's dependencies (per-supernode completion
 //     counters, acquire loads), gather the right-hand side / update vector, do the row.vector products out of shared
 //     memory and publish the results (release);
-//   * tasks are claimed in queue order, so every dependency of a claimed task was claimed earlier by a resident CTA:
+//   * the queue slots are dealt to the CTAs round-robin (CTA c: slots c, c+G, ...), so the chunks of one tree level run on
+//     different CTAs at the same time and every dependency of a slot sits earlier in some resident CTA's list:
 //     no deadlock for any number of resident CTAs (several solver handles may run concurrently).
 // All sums have a fixed order (lane-strided partial sums + shuffle tree, children in ascending order): results are
 // bit-reproducible from run to run.
@@ -132,16 +133,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        unsigned a = 0;
-        if (lane == 0) a = atomicAdd(claim, 1u);
-        unsigned g0 = __shfl_sync(PM, a, 0);
+        // STATIC assignment of the queue slots: CTA c takes the slots c, c + G, c + 2G, ...  Consecutive slots - the chunks of one
+        // tree level - therefore run on different CTAs at the same time (a dynamic queue with claims prefetched one slot ahead
+        // hands consecutive slots to the SAME CTA, which halves the parallelism of the latency-bound top levels), and no
+        // atomics are needed.  Every dependency of a slot has a smaller index and sits earlier in some resident CTA's list:
+        // no deadlock for any number of resident CTAs.
+        const unsigned G = gridDim.x;
+        unsigned g0 = blockIdx.x;
         fetch(0, g0);
-        if (lane == 0) a = atomicAdd(claim, 1u);
         int it = 0, buf = 0;
         while (g0 < (unsigned)ngroups) {
-            const unsigned g1 = __shfl_sync(PM, a, 0);
+            const unsigned g1 = g0 + G;
             fetch(buf ^ 1, g1);
-            if (lane == 0) a = atomicAdd(claim, 1u);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp(PM);
             for (int c = 0; c < SOLVE_GROUP_MAX; ++c) {
@@ -360,6 +363,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
         consumer_sync();  // all results stored, all shared-memory reads of this stage (data, descriptor, vector) done
         if (tid == 0) mbar_arrive(&done[st]);
     }
+}
+
+// right-hand side in the permuted, concatenated numbering of the factors: b_perm[i] = b[gidx[i]] - the gatherers then read
+// contiguous ranges (one latency on the critical path of every supernode instead of two dependent ones)
+__global__ void __launch_bounds__(256) k_gather_rhs(long long n, const double* __restrict__ b, const int* __restrict__ gidx,
+                                                    double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = b[gidx[i]];
 }
 
 // ---- pack the row-major solve panels Sp into the two streamed layouts ----
@@ -609,6 +620,13 @@ void CholBatch::pack_panels(int level, cudaStream_t st) {
 void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st) {
     if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
     if (!n_solve_tasks) return;
+    static const bool pre_gather = std::getenv("DOTGPU_SOLVE_NO_PREGATHER") == nullptr;
+    if (gidx && pre_gather) {
+        k_gather_rhs<<<ceil_div(n_total, 256), 256, 0, st>>>(n_total, b, gidx, rwork.p);
+        count_launch();
+        b = rwork.p;
+        gidx = nullptr;
+    }
     DG_CUDA(cudaMemsetAsync(d_cnt.p, 0, d_cnt.bytes(), st));
     unsigned* claim = d_cnt.p + 3 * (size_t)std::max(nsuper_total, 1);
 #define DG_SOLVE_LAUNCH(NS)                                                                                                         \

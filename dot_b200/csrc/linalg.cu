@@ -373,12 +373,6 @@ __global__ void __launch_bounds__(MD_TPB) k_scatter_dots(int ndof, const int* __
     if ((int)threadIdx.x < P.n) sc[P.out[threadIdx.x]] = res[threadIdx.x];
 }
 
-__global__ void k_negate(long long n, double* __restrict__ p, double* __restrict__ pg) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = -p[i];
-    if (i == 0) pg[0] = -pg[0];
-}
-
 #define EW_LAUNCH(kernel, n, ...)                                              \
     do {                                                                       \
         if ((n) > 0) {                                                         \
@@ -387,7 +381,6 @@ __global__ void k_negate(long long n, double* __restrict__ p, double* __restrict
         }                                                                      \
     } while (0)
 
-void launch_negate(long long n, double* p, double* pg, cudaStream_t st) { EW_LAUNCH(k_negate, n, n, p, pg); }
 void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st) {
     EW_LAUNCH(k_axpy, n, n, out, x0, p, alpha);
 }

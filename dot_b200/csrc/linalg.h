@@ -29,7 +29,6 @@ void launch_spmv_sym(int n, const int* ia, const int* ja, const double* a, const
 int dot_partial_count(long long n);
 // sc[k] = a.b    (partial must hold dot_partial_count(n) doubles, counter one zeroed unsigned)
 void launch_dot(long long n, const double* a, const double* b, double* partial, unsigned* counter, double* sc_out, cudaStream_t st);
-void launch_negate(long long n, double* p, double* pg, cudaStream_t st);  // p = -p, pg[0] = -pg[0] (tests: forced line-search failure)
 void launch_axpy(long long n, double* out, const double* x0, const double* p, double alpha, cudaStream_t st);  // out = x0 + alpha*p
 // initX + xTilde (Optimizer.cpp:472-493, 585-610): x += (dt v + dt^2 g) on free verts
 void launch_warm_start(int nV, double* x, const double* vel, const unsigned char* fixed, double dt, double gx, double gy, double gz,

@@ -96,7 +96,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
     DG_REQUIRE(cfg.dt > 0, "dt must be positive");
     newton = (cfg.flags & DOTGPU_FLAG_NEWTON) != 0;
-    if (const char* e = std::getenv("DOTGPU_DEBUG_ASCENT")) debug_ascent = *e == '1';
+    if (const char* e = std::getenv("DOTGPU_DEBUG_LS_FAIL")) debug_ls_fail = *e == '1';
     if (newton) {
         DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
         cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
@@ -371,7 +371,6 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
             if (!fused) launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
         }
         launch_lbfgs_p(n, p.p, H, sc.p, st);
-        if (debug_ascent) launch_negate(n, p.p, sc.p + SC_PG, st);  // tests only (DOTGPU_DEBUG_ASCENT=1): forces the line search to fail
         // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
         const double* alpha_dev = newton ? nullptr : sc.p + SC_ALPHA;  // Newton: initStepSize = 1 (Optimizer.cpp:1088)
         if (!newton) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
@@ -387,6 +386,9 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                              alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p, true, st);
         fetch_scalars(0, SC_COUNT);  // the one host round trip of an iteration (measured: ~14 us of 240 on bar17K_like)
         double alpha = newton ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
+        // tests only (DOTGPU_DEBUG_LS_FAIL=1): every trial energy reads as +inf, so the step halves until it underflows.  (With real
+        // energies that branch is nearly unreachable: x0 + alpha p rounds to x0 long before alpha reaches 0, and E(x0) > E(x0) is false.)
+        if (debug_ls_fail) Et = INFINITY;
         if (Et > E && alpha > 0.0) {
             // rare: halve until the energy does not increase, then redo the gradient / pair at the accepted point
             while (true) {
@@ -398,6 +400,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                 }
                 launch_axpy_dev(n, x.p, x0.p, p.p, nullptr, alpha, st);
                 Et = energy_at(x.p);
+                if (debug_ls_fail) Et = INFINITY;
                 ++evals;
                 if (!(Et > E)) break;
             }

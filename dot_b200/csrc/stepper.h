@@ -49,7 +49,7 @@ struct Stepper {
     double* h_x = nullptr;           // pinned staging for positions
     double target = 0.0;
     bool newton = false;             // DOTGPU_FLAG_NEWTON
-    bool debug_ascent = false;       // tests only: search along +p0 reversed, so that every trial step raises the energy
+    bool debug_ls_fail = false;      // tests only: every trial energy reads as +inf (exercises the failed-line-search exit)
     double E_last = 0.0;
     std::vector<double> iter_log;    // (alpha, E, |g|^2) rows
     int64_t launches0 = 0;

@@ -540,7 +540,8 @@ def test_history_limits_and_line_search_failure(monkeypatch):
     """(1) history + 1 pair buffers share a scalar table with LB_MAXH = 8 slots per row: 7 pairs is the
     maximum, 8 is rejected; a run with 7 pairs converges to the same minimiser as the default 5.
     (2) a failed line search (step halved to 0, Optimizer.cpp:816-824) ends the time step: converged = 0,
-    line_search_failed = 1, no hang - forced here by searching along the reversed direction (DOTGPU_DEBUG_ASCENT)."""
+    line_search_failed = 1, no hang - forced here by reading every trial energy as +inf (DOTGPU_DEBUG_LS_FAIL); with real
+    energies the branch is nearly unreachable because x0 + alpha p rounds to x0 long before alpha underflows."""
     g = Golden("small_snh_k4_twist")
     V, T = g["setup/V_rest"], g["setup/F"]
     a = D.Anim(g.meta["anim"], V)
@@ -558,16 +559,21 @@ def test_history_limits_and_line_search_failure(monkeypatch):
         xs[h] = x
     for h in (7, 1, 0):
         assert np.abs(xs[h] - xs[5]).max() < 1e-6, h
-    monkeypatch.setenv("DOTGPU_DEBUG_ASCENT", "1")
+    monkeypatch.setenv("DOTGPU_DEBUG_LS_FAIL", "1")
     a = D.Anim(g.meta["anim"], V)
     stp = D.Stepper(V, T, g["setup/epart"], a.fixed_mask(), energy="SNH", k=g.k)
-    monkeypatch.delenv("DOTGPU_DEBUG_ASCENT")
+    monkeypatch.delenv("DOTGPU_DEBUG_LS_FAIL")
     x = V.copy()
     a.step(x, g.meta["dt"])
     fs = stp.frame(x)
     assert fs.line_search_failed == 1 and fs.converged == 0 and fs.iters == 0
     assert fs.halvings > 1000          # 0.1 / 2^h underflows after ~1071 halvings
     assert np.isfinite(x).all()
+    # the stepper stays usable: the next frame (real energies again) converges
+    stp2 = D.Stepper(V, T, g["setup/epart"], D.Anim(g.meta["anim"], V).fixed_mask(), energy="SNH", k=g.k)
+    x2 = V.copy()
+    D.Anim(g.meta["anim"], V).step(x2, g.meta["dt"])
+    assert stp2.frame(x2).converged == 1
 
 
 REAL_MESHES = [
