@@ -106,6 +106,14 @@ def owned_subdomains(k, rank, world):
     return out
 
 
+def balanced_owner(weights, world):
+    """owner[s] of every subdomain: longest-processing-time greedy on the weights (nnz(L_s) in the stepper)."""
+    w = _f64(weights)
+    out = np.empty(w.shape[0], dtype=np.int32)
+    _chk(lib().dotgpu_balanced_owner(w.shape[0], _p(w), int(world), _p(out)))
+    return out
+
+
 def partition(nV, tets, k):
     """METIS<3>::partMesh with the reference's vendored METIS and option vector: element labels [nT] int32 (bit-exact)."""
     T = _i32(tets)
@@ -364,6 +372,10 @@ class Stepper:
 
     def set_state(self, x, velocity=None):
         _chk(lib().dotgpu_stepper_set_state(self.h, _p(_f64(x)), _p(_f64(velocity)) if velocity is not None else None))
+
+    def set_fixed(self, fixed_mask, x_eval=None):
+        """updatePrecondMtrAndFactorize: new Dirichlet set -> re-analysis + refactorisation at x_eval (default: the resident x^n)."""
+        _chk(lib().dotgpu_stepper_set_fixed(self.h, _p(_u8(fixed_mask)), _p(_f64(x_eval)) if x_eval is not None else None))
 
     def get_state(self):
         x, v, xt = np.empty((self.nV, 3)), np.empty(3 * self.nV), np.empty((self.nV, 3))

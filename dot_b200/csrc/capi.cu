@@ -113,6 +113,14 @@ int dotgpu_owned_subdomains(int num_subdomains, int rank, int world, int32_t* ou
     return (int)o.size();
 }
 
+int dotgpu_balanced_owner(int num_subdomains, const double* weight, int world, int32_t* owner_out) {
+    if (num_subdomains < 1 || world < 1 || !weight || !owner_out) return DOTGPU_ERR_INVALID;
+    std::vector<double> w(weight, weight + num_subdomains);
+    std::vector<int> o = balanced_owner(w, world);
+    for (int s = 0; s < num_subdomains; ++s) owner_out[s] = o[s];
+    return DOTGPU_OK;
+}
+
 int dotgpu_mesh_features(int nV, int nT, const double* V_rest, const int32_t* tets, double YM, double PR, double rho,
                          double* DmInv_out, double* vol_out, double* mass_out, double* mu_out, double* lambda_out) {
     API_BEGIN
@@ -503,6 +511,13 @@ int dotgpu_stepper_set_state(dotgpu_stepper* s, const double* x, const double* v
     DG_REQUIRE(s && x, "null argument");
     DG_CUDA(cudaSetDevice(s->s.cfg.device));
     s->s.set_state(x, velocity);
+    API_END
+}
+int dotgpu_stepper_set_fixed(dotgpu_stepper* s, const uint8_t* fixed_mask, const double* x_eval) {
+    API_BEGIN
+    DG_REQUIRE(s && fixed_mask, "null argument");
+    DG_CUDA(cudaSetDevice(s->s.cfg.device));
+    s->s.set_fixed(fixed_mask, x_eval);
     API_END
 }
 int dotgpu_stepper_get_state(dotgpu_stepper* s, double* x, double* velocity, double* xTilde) {

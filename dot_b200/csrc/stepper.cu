@@ -26,6 +26,22 @@ __global__ void k_set_rows(int count, const int* __restrict__ idx, const double*
 }
 }  // namespace
 
+std::vector<int> balanced_owner(const std::vector<double>& weight, int world) {
+    const int k = (int)weight.size();
+    std::vector<int> order(k), own(k, 0);
+    for (int s = 0; s < k; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<double> load(world, 0.0);
+    for (int s : order) {
+        int best = 0;
+        for (int r = 1; r < world; ++r)
+            if (load[r] < load[best]) best = r;
+        own[s] = best;
+        load[best] += weight[s];
+    }
+    return own;
+}
+
 Stepper::~Stepper() {
     if (h_sc) cudaFreeHost(h_sc);
     if (h_x) cudaFreeHost(h_x);
@@ -82,52 +98,52 @@ double Stepper::compute_target() const {
     return t * (dt * dt) * (dt * dt);
 }
 
-void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const double* Vr, const int32_t* T, const int32_t* ep,
-                     const uint8_t* fixed_mask) {
-    cfg = c;
-    nV = nV_;
-    nT = nT_;
-    DG_REQUIRE(nV > 0 && nT > 0 && Vr && T && ep, "null or empty mesh");
-    // history + 1 (S, Y) buffers are in use (the candidate pair lives in a spare slot), and the device scalar table has
-    // LB_MAXH slots per row (linalg.h) -> at most LB_MAXH - 1 pairs
-    static_assert(SC_YP - SC_SG == LB_MAXH && SC_XI - SC_YP == LB_MAXH && SC_SY - SC_XI == LB_MAXH && SC_COUNT == SC_SY + LB_MAXH * LB_MAXH,
-                  "scalar table layout assumes LB_MAXH slots");
-    DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= LB_MAXH - 1, "bad subdomain count / history size (max 7 pairs)");
-    DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
-    DG_REQUIRE(cfg.dt > 0, "dt must be positive");
-    newton = (cfg.flags & DOTGPU_FLAG_NEWTON) != 0;
-    if (const char* e = std::getenv("DOTGPU_DEBUG_LS_FAIL")) debug_ls_fail = *e == '1';
-    if (newton) {
-        DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
-        cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DOTGPU_ERR_NO_DEVICE, "no CUDA device");
-    DG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device index out of range");
-    DG_CUDA(cudaSetDevice(cfg.device));
-    DG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto& e : ev) DG_CUDA(cudaEventCreate(&e));
-    launches0 = g_launch_count;
-    V_rest.assign(Vr, Vr + 3 * (size_t)nV);
-    tets_h.assign(T, T + 4 * (size_t)nT);
-    epart_h.assign(ep, ep + nT);
-    fixed_h.assign(nV, 0);
-    if (fixed_mask) fixed_h.assign(fixed_mask, fixed_mask + nV);
-
-    // ---- mesh features + upload ----
-    std::vector<double> DmInv(9 * (size_t)nT), vol(nT), mu(nT), lam(nT);
-    mass_h.assign(nV, 0.0);
-    mesh_features(nV, nT, V_rest.data(), tets_h.data(), cfg.YM, cfg.PR, cfg.rho, DmInv.data(), vol.data(), mass_h.data(), mu.data(),
-                  lam.data());
-    for (int t = 0; t < nT; ++t) DG_REQUIRE(vol[t] > 0.0, "inverted or degenerate rest tet");
-    mesh.init(cfg.energy_type, nV, nT, tets_h.data(), DmInv.data(), vol.data(), mu.data(), lam.data(), mass_h.data(), fixed_h.data(), st);
-
+// Everything that depends on the Dirichlet set: domain decomposition patterns (fixed rows are identity rows, LinSysSolver.hpp:114-132),
+// matrix fill lists, symbolic analysis of the owned subdomain matrices, the gather / scatter maps of the preconditioner.
+// Runs at creation and again from set_fixed (DOTTimeStepper::updatePrecondMtrAndFactorize, DOTTimeStepper.cpp:185-231).
+void Stepper::setup_decomposition() {
     // ---- domain decomposition, owned subdomains ----
     const int k = cfg.num_subdomains;
     std::vector<char> mask(k, 0);
-    owned = owned_subdomains(k, cfg.rank, cfg.world);
+    if (!owner_locked) owner.assign(k, 0);
+    if (cfg.world > 1 && !owner_locked) {
+        // balance the ranks by sum nnz(L_s): patterns + symbolic analysis of EVERY subdomain (host, OpenMP),
+        // then the same deterministic greedy map on every rank.  DOTGPU_BALANCE=0: plain round-robin.
+        const char* e = std::getenv("DOTGPU_BALANCE");
+        if (e && *e == '0') {
+            for (int s = 0; s < k; ++s) owner[s] = s % cfg.world;
+        } else {
+            DDHost probe;
+            probe.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), nullptr, 0.0, nullptr, false, nullptr);
+            std::vector<double> wgt(k, 0.0);
+#pragma omp parallel for schedule(dynamic)
+            for (int s = 0; s < k; ++s) {
+                Symbolic S;
+                S.analyze(probe.subs[s].pat.n(), probe.subs[s].pat.ia.data(), probe.subs[s].pat.ja.data(), 21);
+                wgt[s] = (double)S.nnz_l;
+            }
+            owner = balanced_owner(wgt, cfg.world);
+        }
+    }
+    owned.clear();
+    for (int s = 0; s < k; ++s)
+        if (owner[s] == cfg.rank) owned.push_back(s);
     for (int s : owned) mask[s] = 1;
     dd.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), V_rest.data(), cfg.rho, mass_h.data(), true, &mask);
+    if (cfg.world > 1 && mesh_own.nT == 0) {
+        // energy / gradient are sharded by tet: this rank evaluates the tets of its own subdomains (the element partition is
+        // disjoint, DOTTimeStepper.cpp:406-450 / SURVEY 8(e)); the sums over the ranks are one all-reduce per evaluation
+        std::vector<int32_t> to;
+        std::vector<double> Do, vo, muo, lo;
+        for (int t = 0; t < nT; ++t)
+            if (mask[epart_h[t]]) {
+                to.insert(to.end(), tets_h.begin() + 4 * (size_t)t, tets_h.begin() + 4 * (size_t)t + 4);
+                Do.insert(Do.end(), DmInv_h.begin() + 9 * (size_t)t, DmInv_h.begin() + 9 * (size_t)t + 9);
+                vo.push_back(vol_h[t]); muo.push_back(mu_h[t]); lo.push_back(lam_h[t]);
+            }
+        DG_REQUIRE(!vo.empty(), "a rank without subdomains (more GPUs than subdomains)");
+        mesh_own.init(cfg.energy_type, nV, (int)vo.size(), to.data(), Do.data(), vo.data(), muo.data(), lo.data(), mass_h.data(), fixed_h.data(), st);
+    }
 
     // ---- concatenated matrices: [global | owned subdomains] ----
     const int nm = 1 + (int)owned.size();
@@ -206,10 +222,74 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
         std::vector<int> du(dd.dup.begin(), dd.dup.end());
         dup.upload(du, st);
     }
+}
+
+// DOTTimeStepper::updatePrecondMtrAndFactorize (DOTTimeStepper.cpp:185-270): the scripted Dirichlet set changed (AnimScripter returns 1,
+// Optimizer.cpp:334-336) -> new patterns + symbolic analysis per subdomain, then Hessians and factorisation at the current positions.
+void Stepper::set_fixed(const uint8_t* fixed_mask, const double* x_eval) {
+    DG_REQUIRE(fixed_mask != nullptr, "null fixed mask");
+    fixed_h.assign(fixed_mask, fixed_mask + nV);
+    mesh.set_fixed(fixed_h.data(), st);
+    owner_locked = true;   // the subdomain -> rank map stays what it was: factors move only inside a rank
+    setup_decomposition();
+    if (cfg.world > 1) mesh_own.set_fixed(fixed_h.data(), st);
+    const double dtsq = cfg.dt * cfg.dt;
+    launch_xtilde(nV, xt.p, xn.p, vel.p, mesh.fixed.p, cfg.dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
+    // the reference evaluates the new preconditioner at result.V, i.e. with this frame's scripted move already applied
+    if (x_eval) x.upload(x_eval, 3 * (size_t)nV, st);
+    else DG_CUDA(cudaMemcpyAsync(x.p, xn.p, 3 * (size_t)nV * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    refresh();
+    chol.check_status(st);
+}
+
+void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const double* Vr, const int32_t* T, const int32_t* ep,
+                     const uint8_t* fixed_mask) {
+    cfg = c;
+    nV = nV_;
+    nT = nT_;
+    DG_REQUIRE(nV > 0 && nT > 0 && Vr && T && ep, "null or empty mesh");
+    // history + 1 (S, Y) buffers are in use (the candidate pair lives in a spare slot), and the device scalar table has
+    // LB_MAXH slots per row (linalg.h) -> at most LB_MAXH - 1 pairs
+    static_assert(SC_YP - SC_SG == LB_MAXH && SC_XI - SC_YP == LB_MAXH && SC_SY - SC_XI == LB_MAXH && SC_COUNT == SC_SY + LB_MAXH * LB_MAXH,
+                  "scalar table layout assumes LB_MAXH slots");
+    DG_REQUIRE(cfg.num_subdomains >= 1 && cfg.history >= 0 && cfg.history <= LB_MAXH - 1, "bad subdomain count / history size (max 7 pairs)");
+    DG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
+    DG_REQUIRE(cfg.dt > 0, "dt must be positive");
+    newton = (cfg.flags & DOTGPU_FLAG_NEWTON) != 0;
+    if (const char* e = std::getenv("DOTGPU_DEBUG_LS_FAIL")) debug_ls_fail = *e == '1';
+    if (newton) {
+        DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
+        cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DOTGPU_ERR_NO_DEVICE, "no CUDA device");
+    DG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device index out of range");
+    DG_CUDA(cudaSetDevice(cfg.device));
+    DG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) DG_CUDA(cudaEventCreate(&e));
+    launches0 = g_launch_count;
+    V_rest.assign(Vr, Vr + 3 * (size_t)nV);
+    tets_h.assign(T, T + 4 * (size_t)nT);
+    epart_h.assign(ep, ep + nT);
+    fixed_h.assign(nV, 0);
+    if (fixed_mask) fixed_h.assign(fixed_mask, fixed_mask + nV);
+
+    // ---- mesh features + upload ----
+    DmInv_h.assign(9 * (size_t)nT, 0.0);
+    vol_h.assign(nT, 0.0);
+    mu_h.assign(nT, 0.0);
+    lam_h.assign(nT, 0.0);
+    mass_h.assign(nV, 0.0);
+    mesh_features(nV, nT, V_rest.data(), tets_h.data(), cfg.YM, cfg.PR, cfg.rho, DmInv_h.data(), vol_h.data(), mass_h.data(), mu_h.data(),
+                  lam_h.data());
+    for (int t = 0; t < nT; ++t) DG_REQUIRE(vol_h[t] > 0.0, "inverted or degenerate rest tet");
+    mesh.init(cfg.energy_type, nV, nT, tets_h.data(), DmInv_h.data(), vol_h.data(), mu_h.data(), lam_h.data(), mass_h.data(), fixed_h.data(), st);
+
+    setup_decomposition();
     // ---- vectors ----
     const size_t n3 = 3 * (size_t)nV;
     for (DevBuf<double>* b : {&x, &x0, &xn, &xt, &vel, &g, &g_old, &q, &p}) {
-        b->alloc(n3);
+        b->alloc(n3 + 1);   // + 1: the energy rides behind the gradient in the multi-GPU all-reduce
         b->zero(st);
     }
     xperm.alloc(std::max<int64_t>(chol.n_total, 1));
@@ -249,12 +329,32 @@ void Stepper::fetch_scalars(int first, int count) {
 }
 
 double Stepper::energy_at(const double* x_dev) {
-    launch_energy(mesh, x_dev, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st);
+    if (cfg.world > 1) {  // partial energy of the owned tets (+ the inertia term on rank 0), summed over the ranks
+        launch_energy(mesh_own, x_dev, cfg.rank == 0 ? xt.p : nullptr, cfg.dt * cfg.dt, sc.p + SC_E, st);
+        comm->all_reduce_sum(sc.p + SC_E, 1, st);
+    } else {
+        launch_energy(mesh, x_dev, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st);
+    }
     fetch_scalars(SC_E, 1);
     return h_sc[SC_E];
 }
 
-void Stepper::gradient_at(const double* x_dev, double* g_dev) { launch_gradient(mesh, x_dev, xt.p, cfg.dt * cfg.dt, g_dev, st); }
+void Stepper::gradient_at(const double* x_dev, double* g_dev) {
+    if (cfg.world > 1) {
+        launch_gradient(mesh_own, x_dev, cfg.rank == 0 ? xt.p : nullptr, cfg.dt * cfg.dt, g_dev, st);
+        comm->all_reduce_sum(g_dev, 3LL * nV, st);
+    } else {
+        launch_gradient(mesh, x_dev, xt.p, cfg.dt * cfg.dt, g_dev, st);
+    }
+}
+
+void Stepper::eval_sharded(const double* x_dev, double* G) {
+    const long long n3 = 3LL * nV;
+    const double* xtp = cfg.rank == 0 ? xt.p : nullptr;
+    launch_energy(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G + n3, st);
+    launch_gradient(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G, st);
+    comm->all_reduce_sum(G, n3 + 1, st);
+}
 
 void Stepper::refresh() {
     launch_elem_hessians(mesh, x.p, cfg.dt * cfg.dt, true, st);
@@ -330,9 +430,14 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     int halvings = 0, evals = 0;
     // initX(warmStart = 2)
     launch_warm_start(nV, x.p, vel.p, mesh.fixed.p, dt, cfg.gravity[0] * dtsq, cfg.gravity[1] * dtsq, cfg.gravity[2] * dtsq, st);
-    launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
+    if (cfg.world > 1) {
+        eval_sharded(x.p, g.p);
+        DG_CUDA(cudaMemcpyAsync(sc.p + SC_E, g.p + n3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        launch_energy(mesh, x.p, xt.p, dtsq, sc.p + SC_E, st);
+        gradient_at(x.p, g.p);
+    }
     ++evals;
-    gradient_at(x.p, g.p);
     launch_dot(n, g.p, g.p, dot_partial.p, counter.p, sc.p + SC_GG, st);
     fetch_scalars(SC_E, 2);
     double E = h_sc[SC_E], gg = h_sc[SC_GG];
@@ -382,8 +487,21 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         // energy AND gradient at the trial point in one pass over the tets (g_old is the spare buffer until the step is accepted)
         // + new pair + the next iteration's dots
         const int sl = cfg.history > 0 ? free_slots.back() : -1;  // history+1 buffers: a candidate slot is always free
-        launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl,
-                             alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p, true, st);
+        const bool multi = cfg.world > 1;
+        // one GPU: gradient + energy + pair + dots fused (k_grad_vertex_pair).  Several GPUs: each rank evaluates its own tets,
+        // one all-reduce of [g ; E], then the pair and its dots from the reduced gradient (s_i . g follows at the next iteration's start)
+        auto grad_pair = [&](const double* a_dev, double a_host, bool with_energy) {
+            if (!multi) {
+                launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl,
+                                     a_dev, a_host, H, md_partial.p, counter.p, sc.p, with_energy, st);
+                return;
+            }
+            eval_sharded(x.p, g_old.p);
+            if (with_energy) DG_CUDA(cudaMemcpyAsync(sc.p + SC_E, g_old.p + n3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, a_dev, a_host, H, md_partial.p,
+                             counter.p, sc.p, st);
+        };
+        grad_pair(alpha_dev, 1.0, true);
         fetch_scalars(0, SC_COUNT);  // the one host round trip of an iteration (measured: ~14 us of 240 on bar17K_like)
         double alpha = newton ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
         // tests only (DOTGPU_DEBUG_LS_FAIL=1): every trial energy reads as +inf, so the step halves until it underflows.  (With real
@@ -404,14 +522,13 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                 ++evals;
                 if (!(Et > E)) break;
             }
-            launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, nullptr,
-                                 alpha, H, md_partial.p, counter.p, sc.p, false, st);
+            grad_pair(nullptr, alpha, false);
             fetch_scalars(0, SC_COUNT);
         }
         E = Et;
         std::swap(g.p, g_old.p);
         gg = h_sc[SC_GG];
-        sg_valid = true;  // sc[SC_SG + slot] now holds s_i . g for every pair that can be in the next history
+        sg_valid = !multi;  // one GPU: sc[SC_SG + slot] now holds s_i . g for every pair that can be in the next history
         // ---- history update (DOTTimeStepper.cpp:476-493): keep the pair iff y.s > 0, then drop the oldest beyond `history` ----
         if (sl >= 0 && h_sc[SC_YS_NEW] > 0.0) {
             free_slots.pop_back();
@@ -494,8 +611,8 @@ double Stepper::time_kernels(int which, int reps) {
     for (int r = -1; r < reps; ++r) {
         if (r == 0) DG_CUDA(cudaEventRecord(a, st));
         switch (which) {
-            case 0: launch_energy(mesh, x.p, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st); break;
-            case 1: gradient_at(x.p, g_old.p); break;
+            case 0: launch_energy(emesh(), x.p, xt.p, cfg.dt * cfg.dt, sc.p + SC_E, st); break;
+            case 1: launch_gradient(emesh(), x.p, xt.p, cfg.dt * cfg.dt, g_old.p, st); break;
             case 2: launch_elem_hessians(mesh, x.p, cfg.dt * cfg.dt, true, st); break;
             case 3: launch_fill(fill, mesh.He.p, a_all.p, st); break;
             case 4: if (!owned.empty()) chol.factorize(a_all.p + a_off[1], st); break;

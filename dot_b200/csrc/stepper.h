@@ -15,25 +15,35 @@ namespace dotgpu {
 
 struct Comm;  // NCCL communicator wrapper (comm.cpp)
 
-// subdomains are dealt round-robin to ranks (every rank factors / solves its own ones)
+// static round-robin map of subdomains to ranks (the fallback / bookkeeping map of dotgpu_owned_subdomains; a stepper balances
+// its ranks by nnz(L) instead, see balanced_owner)
 inline std::vector<int> owned_subdomains(int k, int rank, int world) {
     std::vector<int> o;
     for (int s = 0; s < k; ++s)
         if (s % world == rank) o.push_back(s);
     return o;
 }
+// whole subdomains are assigned to GPUs balancing sum nnz(L_s): longest-processing-time greedy on the given weights
+// (deterministic: ties by lower rank / lower subdomain id, so every rank computes the same map).  Returns owner[s].
+std::vector<int> balanced_owner(const std::vector<double>& weight, int world);
 
 struct Stepper {
     dotgpu_stepper_config cfg;
     int nV = 0, nT = 0;
     cudaStream_t st = nullptr;
-    std::vector<double> V_rest, mass_h;
+    std::vector<double> V_rest, mass_h, DmInv_h, vol_h, mu_h, lam_h;
     std::vector<int32_t> tets_h, epart_h;
     std::vector<uint8_t> fixed_h;
     DDHost dd;
     std::vector<int> owned;          // subdomain ids handled by this rank, ascending
     std::vector<int64_t> a_off;      // value offsets: [0]=global, [1+i]=owned[i]
-    DeviceMesh mesh;
+    DeviceMesh mesh;                 // all tets (elemental Hessians of the refresh; energy / gradient on one GPU)
+    DeviceMesh mesh_own;             // world > 1: the tets of the owned subdomains only - energy / gradient are sharded by tet
+    DeviceMesh& emesh() { return cfg.world > 1 ? mesh_own : mesh; }
+    std::vector<int> owner;          // world > 1: owner[s] = rank of subdomain s
+    bool owner_locked = false;
+    void setup_decomposition();      // everything that depends on the Dirichlet set
+    void set_fixed(const uint8_t* fixed_mask, const double* x_eval);
     DevBuf<double> a_all;
     DevBuf<int> g_ia, g_ja;
     DeviceFill fill;
@@ -56,7 +66,9 @@ struct Stepper {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> pc_ev;  // event pairs around the preconditioner applications of a frame
     std::unique_ptr<Comm> comm;
-    DevBuf<unsigned char> own_tet;   // multi-GPU: 1 if this rank sums the tet into energy/gradient
+    // world > 1: energy and gradient of the incremental potential at x_dev, summed over the ranks: G[0..3nV) = gradient,
+    // G[3nV] = energy (one all-reduce of 3nV + 1 doubles; the inertia terms are added by rank 0 only)
+    void eval_sharded(const double* x_dev, double* G);
 
     ~Stepper();
     void create(const dotgpu_stepper_config& c, int nV, int nT, const double* V_rest, const int32_t* tets, const int32_t* epart,

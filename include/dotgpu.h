@@ -183,9 +183,13 @@ typedef struct dotgpu_stepper_config {
     int32_t flags;            /* DOTGPU_FLAG_* */
 } dotgpu_stepper_config;
 void dotgpu_stepper_default_config(dotgpu_stepper_config* c);
-/* Static map of subdomains to ranks (the multi-GPU sharding of the path): writes the ascending list of
- * subdomain ids rank `rank` of `world` factors and solves; returns their number (or a negative error code).  out may be NULL. */
+/* Round-robin map of subdomains to ranks (bookkeeping / DOTGPU_BALANCE=0; see dotgpu_balanced_owner and
+ * dotgpu_stepper_get_owned for what a stepper uses): writes the ascending list of
+ * subdomain ids rank `rank` of `world` would factor and solve; returns their number (or a negative error code).  out may be NULL. */
 int dotgpu_owned_subdomains(int num_subdomains, int rank, int world, int32_t* out);
+/* The map a multi-GPU stepper actually uses: whole subdomains to ranks, balancing the given weights (the stepper passes nnz(L_s) of
+ * its own symbolic analysis) by longest-processing-time greedy; deterministic, so every rank computes the same owner_out [k]. */
+int dotgpu_balanced_owner(int num_subdomains, const double* weight, int world, int32_t* owner_out);
 /* rank 0 calls this and broadcasts the 128 bytes (e.g. torch.distributed) before every rank creates its stepper */
 int dotgpu_nccl_unique_id(void* out128);
 
@@ -219,6 +223,11 @@ int dotgpu_stepper_frame_resident(dotgpu_stepper* s, const int32_t* fixed_idx, c
 /* restart (Optimizer ctor :126-177 reading `status<n>`): positions + velocity; refreshes the Hessians at x. */
 int dotgpu_stepper_set_state(dotgpu_stepper* s, const double* x, const double* velocity);
 int dotgpu_stepper_get_state(dotgpu_stepper* s, double* x, double* velocity, double* xTilde);
+/* DOTTimeStepper::updatePrecondMtrAndFactorize (DOTTimeStepper.cpp:185-270; called from Optimizer::solve when the AnimScripter changes the
+ * Dirichlet set, Optimizer.cpp:334-336): new Dirichlet set fixed_mask [nV] -> patterns, fill lists and symbolic analysis of every owned
+ * subdomain are rebuilt, then the Hessians and the factorisation at x_eval [nV*3] (the reference uses result.V with this frame's scripted
+ * move applied; NULL: the resident x^n).  The subdomain -> rank map is kept. */
+int dotgpu_stepper_set_fixed(dotgpu_stepper* s, const uint8_t* fixed_mask, const double* x_eval);
 /* per-iteration log of the last frame: rows (alpha, E, |g|^2), row 0 = after initX; returns rows written */
 int dotgpu_stepper_get_iter_log(dotgpu_stepper* s, double* out, int max_rows);
 /* checkers: matrix values after the last refresh (s=-1 global, else subdomain index; subdomains of other

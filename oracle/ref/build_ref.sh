@@ -90,7 +90,7 @@ if [ -f "$REPO/dot_b200/libdotgpu.so" ]; then
   dotgpu_cc() {
     local src="$1"
     local o="$OBJ/dot_gpu/$(basename "${src%.cpp}").o"
-    [ "$o" -nt "$src" ] && [ "$o" -nt "$REPO/integration/dropin/CHOLMODSolver.hpp" ] && [ "$o" -nt "$REPO/integration/dropin/GpuEnergy.hpp" ] \
+    [ "$o" -nt "$src" ] && [ "$o" -nt "$REPO/integration/dropin/CHOLMODSolver.hpp" ] && [ "$o" -nt "$REPO/integration/dropin/GpuEnergy.hpp" ] && [ "$o" -nt "$REPO/integration/dropin/GpuDOTStepper.hpp" ] && [ "$o" -nt "$REPO/include/dotgpu.h" ] \
       || g++ $CXXF -DDOTGPU_DROPIN $GINC -c "$src" -o "$o"
   }
   export -f dotgpu_cc; export GINC REPO

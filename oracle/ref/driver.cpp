@@ -49,6 +49,7 @@
 // drop-in build (oracle/_ref/dot_ref_gpu): the same unmodified reference steppers, but "CHOLMODSolver.hpp" above resolved to
 // integration/dropin/CHOLMODSolver.hpp (libdotgpu-backed LinSysSolver) and the energy object is GpuEnergy<reference energy>.
 #include "GpuEnergy.hpp"
+#include "GpuDOTStepper.hpp"
 #endif
 
 // ---- globals the reference translation units expect (main.cpp:27-88) ----
@@ -293,7 +294,7 @@ static void usage()
     std::cerr << "dot_ref --script <file.txt> [--mesh <file.msh>] [--energy SNH|FCR] [--parts K] [--stepper DOT|Newton]\n"
                  "        [--tol T] [--dt DT] [--anim <script name>] [--frames N] [--threads N] [--quiet] [--labels-only]\n"
                  "        [--dump-dir D] [--dump-frames a,b,c] [--he-cap N] [--kernel-state V.npy] [--stats-json file]\n"
-                 "        [--final-V V.npy] [--full-precision]\n";
+                 "        [--final-V V.npy] [--full-precision] [--resident (drop-in build: GpuDOTStepper)]\n";
 }
 
 int main(int argc, char** argv)
@@ -303,7 +304,7 @@ int main(int argc, char** argv)
     int parts = -1, frames = 10, threads = 0;
     long heCap = -1;
     double tol = -1, dtOverride = -1;
-    bool quiet = false, labelsOnly = false, cpuEnergy = false;
+    bool quiet = false, labelsOnly = false, cpuEnergy = false, resident = false;
     std::set<int> dumpFrames;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -321,6 +322,7 @@ int main(int argc, char** argv)
         else if (a == "--quiet") quiet = true;
         else if (a == "--labels-only") labelsOnly = true;
         else if (a == "--cpu-energy") cpuEnergy = true;  // drop-in build only: keep the reference's CPU energy, GPU solvers only
+        else if (a == "--resident") resident = true;      // drop-in build only: GpuDOTStepper (device-resident stepper) instead of DOTTimeStepper
         else if (a == "--dump-dir") dumpDir = next();
         else if (a == "--he-cap") heCap = std::stol(next());
         else if (a == "--kernel-state") kernelState = next();
@@ -436,6 +438,12 @@ int main(int argc, char** argv)
     auto t0 = std::chrono::steady_clock::now();
     Opt* opt = nullptr;
     DotOpt* dot = nullptr;
+#ifdef DOTGPU_DROPIN
+    if (resident) {
+        if (!dumpDir.empty() || !kernelState.empty()) { std::cerr << "--resident cannot be combined with the dump modes" << std::endl; return 1; }
+        opt = new DOT::GpuDOTStepper(*temp, energyTerms, energyParams, false, config);
+    } else
+#endif
     switch (config.timeStepperType) {
         case DOT::TST_NEWTON: opt = new Opt(*temp, energyTerms, energyParams, false, config); break;
         case DOT::TST_DOT: dot = new DotOpt(*temp, energyTerms, energyParams, false, config); opt = dot; break;

@@ -620,7 +620,7 @@ def test_full_size_position_parity_on_reference_meshes(tmp_path, mesh, energy, k
     assert abs(iters - st["inner_iters"]) <= 0.15 * st["inner_iters"] + 3, (iters, st["inner_iters"])
 
 
-def _run_ref_final(exe, tmp, script, frames, tol, threads=None):
+def _run_ref_final(exe, tmp, script, frames, tol, threads=None, extra=()):
     import json
     import os
     import subprocess
@@ -631,8 +631,110 @@ def _run_ref_final(exe, tmp, script, frames, tol, threads=None):
     if os.path.exists(blas):
         env["LD_LIBRARY_PATH"] = open(blas).read().strip() + ":" + env.get("LD_LIBRARY_PATH", "")
     fv = os.path.join(tmp, "finalV.npy")
-    out = subprocess.run([exe, "--script", script, "--frames", str(frames), "--quiet", "--threads", nthr, "--tol", repr(tol), "--final-V", fv],
+    out = subprocess.run([exe, "--script", script, "--frames", str(frames), "--quiet", "--threads", nthr, "--tol", repr(tol), "--final-V", fv] + list(extra),
                          cwd=tmp, env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stderr[-2000:]
     st = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     return st, np.load(fv)
+
+
+@pytest.mark.parametrize("name,frames", [("small_snh_k4_twist", 4), ("small_fcr_k3_tsns_dt200", 3)])
+def test_two_ranks_match_one_rank(tmp_path, name, frames):
+    """SURVEY 8(e) on hardware: 2 ranks (one per GPU, NCCL) - subdomains (factor + solves) and tets (energy / gradient) sharded,
+    [g ; E] and the search direction all-reduced every iteration - against the same run on 1 rank, both at tol 1e-9: positions
+    to 1e-7 of the bounding box (the reduction order of g differs between N = 1 and N = 2, so paths agree to rounding, not bitwise),
+    every rank ends with identical positions.  The second case goes through the line-search halving branch on 2 ranks.  Needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if D.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    g = Golden(name)
+    V = g["setup/V_rest"]
+    stp, anim = _stepper(g, rel_tol=1e-9)
+    x1 = V.copy()
+    h1 = 0
+    for f in range(frames):
+        anim.step(x1, g.meta["dt"])
+        fs = stp.frame(x1)
+        assert fs.converged == 1
+        h1 += fs.halvings
+    del stp
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "mg")
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(here, "multi_gpu_worker.py"), name, str(frames), "1e-9", out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    z0, z1 = np.load(out + ".rank0.npz"), np.load(out + ".rank1.npz")
+    assert np.array_equal(z0["x"], z1["x"])                       # replicas stay bit-identical across the ranks
+    assert sorted(z0["owned"].tolist() + z1["owned"].tolist()) == list(range(g.k))
+    assert np.abs(z0["x"] - x1).max() < 1e-7
+    if name.endswith("dt200"):
+        assert int(z0["halvings"]) > 0 and h1 > 0
+
+
+@pytest.mark.parametrize("preset,energy,k,anim", [("bar_small", "SNH", 4, "twist"), ("bar2K", "FCR", 6, "twistnsns")])
+def test_dropin_resident_GpuDOTStepper_vs_reference_binary(tmp_path, preset, energy, k, anim):
+    """SURVEY 8(b), the performance boundary COMPILED: integration/dropin/GpuDOTStepper.hpp (an Optimizer<3> subclass over
+    dotgpu_stepper_*, labels from dotgpu_partition = the reference's vendored METIS) linked with the unmodified reference sources
+    (oracle/_ref/dot_ref_gpu --resident) against the all-CPU reference binary: same script from rest, tol 1e-9, positions after 4
+    frames to 1e-6 of the bounding box, same amount of work."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cpu, gpu = os.path.join(root, "oracle", "_ref", "dot_ref"), os.path.join(root, "oracle", "_ref", "dot_ref_gpu")
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref binaries not built")
+    if not os.path.exists(os.path.join(os.path.dirname(D.lib_path()), "libdotmetis.so")):
+        pytest.skip("libdotmetis.so not built")
+    tmp = str(tmp_path)
+    V, T = meshgen.preset(preset)
+    msh = os.path.join(tmp, "m.msh")
+    meshgen.write_msh(msh, V, T)
+    script = os.path.join(tmp, "s.txt")
+    meshgen.write_script(script, msh, energy=energy, parts=k, anim=anim)
+    st_c, Vc = _run_ref_final(cpu, tmp, script, 4, 1e-9)
+    os.rename(os.path.join(tmp, "finalV.npy"), os.path.join(tmp, "finalV_cpu.npy"))
+    env_ld = os.environ.get("LD_LIBRARY_PATH", "")
+    os.environ["LD_LIBRARY_PATH"] = os.path.dirname(D.lib_path()) + ":" + env_ld
+    try:
+        st_g, Vg = _run_ref_final(gpu, tmp, script, 4, 1e-9, extra=["--resident"])
+    finally:
+        os.environ["LD_LIBRARY_PATH"] = env_ld
+    assert abs(st_g["targetGRes"] - st_c["targetGRes"]) <= 1e-10 * st_c["targetGRes"]
+    assert np.abs(Vg - Vc).max() < 1e-6
+    assert abs(st_g["inner_iters"] - st_c["inner_iters"]) <= 0.15 * st_c["inner_iters"] + 3
+
+
+def test_set_fixed_reanalysis_matches_a_fresh_stepper():
+    """DOTTimeStepper::updatePrecondMtrAndFactorize (DOTTimeStepper.cpp:185-270) = dotgpu_stepper_set_fixed: after the Dirichlet set
+    changes mid-run (one handle released) the stepper continues exactly like a stepper created with the new set and restarted from the
+    same (x, v): bit-identical positions, and the released vertices start to move."""
+    g = Golden("small_snh_k4_twist")
+    V, T, ep = g["setup/V_rest"], g["setup/F"], g["setup/epart"]
+    a = D.Anim("twist", V)
+    fm = a.fixed_mask()
+    stp = D.Stepper(V, T, ep, fm, energy="SNH", k=g.k)
+    x = V.copy()
+    for f in range(2):
+        a.step(x, 0.025)
+        assert stp.frame(x).converged == 1
+    xs, vs, _ = stp.get_state()
+    fm2 = fm.copy()
+    right = np.nonzero((fm > 0) & (V[:, 0] > 0.5 * V[:, 0].max()))[0]
+    fm2[right] = 0                                   # release the right handle
+    stp.set_fixed(fm2, xs)
+    fresh = D.Stepper(V, T, ep, fm2, energy="SNH", k=g.k)
+    fresh.set_state(xs, vs)
+    xa, xb = xs.copy(), xs.copy()
+    for f in range(2):
+        fa, fb = stp.frame(xa), fresh.frame(xb)
+        assert fa.converged == 1 and fb.converged == 1 and fa.iters == fb.iters
+        assert np.array_equal(xa, xb)
+    assert np.abs(xa[right] - xs[right]).max() > 1e-6   # the released handle moves now
+    assert np.array_equal(xa[fm2 > 0], xs[fm2 > 0])    # the other one stays where the script left it
