@@ -4,9 +4,9 @@ Does what the reference's `DOT_bin 100 <script>` does for the scripts inside the
 DOT k | Newton, `shape input <msh>`): load + rotate + normalise the mesh (main.cpp:673-712), scripted Dirichlet motion, one
 converged time step per frame, `iterStats.txt`, restart files and the final mesh in the output folder.
 
-Subdomain labels: the reference partitions with METIS 5.1.0, which cannot ship with this repo.  Give the reference's labels with
-`--labels file.npy|.npz` (bit-exact subdomains, e.g. from oracle/_ref/dot_ref --labels-only) or let `--partition rcb` build a
-coordinate-bisection decomposition (valid, converges to the same frames, but not the reference's labels).
+Subdomain labels: `dotgpu_partition` (the reference's vendored METIS 5.1.0 behind the C ABI, bit-exact labels) when libdotmetis.so
+has been built; otherwise give labels with `--labels file.npy|.npz` or fall back to a coordinate-bisection decomposition
+(`--partition rcb`: valid, converges to the same frames, but not the reference's labels).
 """
 from __future__ import annotations
 
@@ -42,6 +42,10 @@ def main(argv=None):
     V = io.rotate_model(V, s.rot_axis, s.rot_deg)
     V = meshgen.normalise_like_loader(V, s.size)
     newton = s.time_stepper == "Newton"
+    if s.warm_start != 2:
+        sys.exit("warmStart %d is outside the GPU path: the resident stepper implements initX(2) (x^n + dt v^n + dt^2 g), Optimizer.cpp:472-493" % s.warm_start)
+    if s.unknown:
+        print("warning: script keys ignored by the GPU path: %s" % ", ".join(s.unknown), file=sys.stderr)
     if newton:
         k, epart = 1, np.zeros(T.shape[0], dtype=np.int32)
     else:
@@ -52,7 +56,10 @@ def main(argv=None):
             if epart.shape[0] != T.shape[0] or epart.min() < 0 or epart.max() >= k:
                 sys.exit("labels do not match the mesh / partition count")
         else:
-            epart = io.partition_rcb(V, T, k)
+            try:   # the reference's vendored METIS behind the C ABI (bit-exact labels); RCB only where libdotmetis.so is absent
+                epart = D.partition(V.shape[0], T, k)
+            except D.DotGpuError:
+                epart = io.partition_rcb(V, T, k)
     anim = D.Anim(s.script, V, s.handle_ratio)
     fixed = anim.fixed_mask()
     if s.script == "null":
@@ -71,27 +78,33 @@ def main(argv=None):
         frame0 = st["timestep"]
     setup = time.time() - t0
     os.makedirs(a.out, exist_ok=True)
-    stats = io.IterStatsWriter(os.path.join(a.out, "iterStats.txt"))
+    stats = io.IterStatsWriter(os.path.join(a.out, "iterStats.txt"), s.time_stepper)
     if SF.shape[0] and not newton:
         io.write_label_obj(os.path.join(a.out, "label.obj"), SF, io.surface_to_tet(T, SF), epart)
     nframes = a.frames if a.frames is not None else s.num_frames() - frame0
     iters = 0
     t0 = time.time()
+    cur_tol = s.rel_tol(0)
+    dxe = np.zeros_like(x)
     for f in range(frame0, frame0 + nframes):
-        stp.set_rel_tol(s.rel_tol(f))
+        if s.rel_tol(f) != cur_tol:          # Optimizer::setRelGL2Tol only when the script changes it (recomputes targetGRes)
+            cur_tol = s.rel_tol(f)
+            stp.set_rel_tol(cur_tol)
+        xt_prev = stp.get_state()[2]          # xTilta of this time step (dx_Elastic = x - xTilta, Optimizer.cpp:356)
         anim.step(x, s.dt)
         fs = stp.frame(x)
+        dxe = x - xt_prev
         iters += fs.iters
         stats.frame(f, stp.iter_log())
         if not fs.converged:
             print("frame %d did not converge (|g|^2 = %g > %g)" % (f, fs.grad_sqnorm, fs.target), file=sys.stderr)
         if a.save_every and (f + 1) % a.save_every == 0:
             xs, vs, _ = stp.get_state()
-            io.write_status(os.path.join(a.out, "status%d" % (f + 1)), f + 1, xs, vs)
+            io.write_status(os.path.join(a.out, "status%d" % (f + 1)), f + 1, xs, vs, dxe)
     wall = time.time() - t0
     stats.close()
     xs, vs, _ = stp.get_state()
-    io.write_status(os.path.join(a.out, "status%d" % (frame0 + nframes)), frame0 + nframes, xs, vs)
+    io.write_status(os.path.join(a.out, "status%d" % (frame0 + nframes)), frame0 + nframes, xs, vs, dxe)
     meshgen.write_msh(os.path.join(a.out, "finalResult_mesh.msh"), xs, T, SF if SF.shape[0] else None)
     info = {"frames": nframes, "inner_iters": iters, "fps": nframes / wall if wall > 0 else None, "setup_sec": setup, "nT": int(T.shape[0]),
             "nV": int(V.shape[0]), "parts": int(k), "energy": s.energy, "timeStepper": s.time_stepper, "sumV": float(xs.sum()),

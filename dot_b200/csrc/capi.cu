@@ -591,7 +591,7 @@ int dotgpu_stepper_get_target(dotgpu_stepper* s, double* target) {
 int dotgpu_stepper_set_rel_tol(dotgpu_stepper* s, double rel_tol) {
     if (!s || !(rel_tol > 0.0)) return DOTGPU_ERR_INVALID;
     s->s.cfg.rel_tol = rel_tol;
-    s->s.target = s->s.compute_target();
+    s->s.target = s->s.target_per_tolsq * rel_tol * rel_tol;  // O(1): the O(nT) geometry factor was computed at create time
     return DOTGPU_OK;
 }
 int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* ms_out) {

@@ -313,6 +313,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
         comm->init(cfg.nccl_unique_id, cfg.rank, cfg.world);
     }
     target = compute_target();
+    target_per_tolsq = target / (cfg.rel_tol * cfg.rel_tol);  // the geometry / material factor: set_rel_tol only rescales it
     // ---- precompute(): rest-state energy, Hessians, factorisation (DOTTimeStepper.cpp:150-182) ----
     x.upload(V_rest.data(), n3, st);
     DG_CUDA(cudaMemcpyAsync(xn.p, x.p, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));

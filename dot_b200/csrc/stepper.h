@@ -57,7 +57,7 @@ struct Stepper {
     DevBuf<unsigned> counter;
     double* h_sc = nullptr;          // pinned mirror
     double* h_x = nullptr;           // pinned staging for positions
-    double target = 0.0;
+    double target = 0.0, target_per_tolsq = 0.0;
     bool newton = false;             // DOTGPU_FLAG_NEWTON
     bool debug_ls_fail = false;      // tests only: every trial energy reads as +inf (exercises the failed-line-search exit)
     double E_last = 0.0;

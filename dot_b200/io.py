@@ -35,8 +35,8 @@ class Script:
     size: float = 1.0                 # longest bounding-box edge after loading (main.cpp:709)
     duration: float = 10.0
     dt: float = 0.025
-    rho: float = 1000.0
-    YM: float = 1e5
+    rho: float = 1.0                  # Config::Config defaults (Config.cpp:33-37): rho 1, YM 100, PR 0.4 - the shipped scripts set their own
+    YM: float = 100.0
     PR: float = 0.4
     with_gravity: bool = True
     script: str = "null"
@@ -196,6 +196,22 @@ def write_status(path: str, timestep: int, x: np.ndarray, velocity: np.ndarray, 
         f.write("".join("%e %e %e\n" % (r[0], r[1], r[2]) for r in d))
 
 
+def write_msh_reference(path: str, V: np.ndarray, T: np.ndarray, SF: np.ndarray) -> None:
+    """The .msh file exactly as IglUtils::saveTetMesh writes it (IglUtils.cpp:627-679; coordinates with %le, i.e. 7 significant
+    digits - `meshgen.write_msh` writes the same dialect with %.17g for loss-free round trips)."""
+    lo, hi = V.min(axis=0), V.max(axis=0)
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n4 0 8\n$EndMeshFormat\n$Entities\n0 0 0 1\n")
+        f.write("0 %e %e %e %e %e %e 0 0\n$EndEntities\n" % (lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]))
+        f.write("$Nodes\n1 %d\n0 3 0 %d\n" % (V.shape[0], V.shape[0]))
+        f.write("".join("%d %e %e %e\n" % (i + 1, v[0], v[1], v[2]) for i, v in enumerate(V)))
+        f.write("$EndNodes\n$Elements\n1 %d\n0 3 4 %d\n" % (T.shape[0], T.shape[0]))
+        f.write("".join("%d %d %d %d %d\n" % (i + 1, t[0] + 1, t[1] + 1, t[2] + 1, t[3] + 1) for i, t in enumerate(T)))
+        f.write("$EndElements\n$Surface\n%d\n" % SF.shape[0])
+        f.write("".join("%d %d %d\n" % (s_[0] + 1, s_[1] + 1, s_[2] + 1) for s_ in SF))
+        f.write("$EndSurface\n")
+
+
 def read_status(path: str):
     """Returns dict(timestep, position [nV,3], velocity [3 nV], dx_Elastic [nV,3] or None)."""
     toks = open(path).read().split()
@@ -224,13 +240,18 @@ def read_status(path: str):
 
 
 class IterStatsWriter:
-    def __init__(self, path: str):
+    """iterStats.txt exactly as the reference's steppers stream it (default ostream formatting = %g):
+    `timeStepper DOT`    -> `<frame> <alpha> <E> <|g|^2>`          (DOTTimeStepper.cpp:298, 306, 329; Optimizer.cpp:862)
+    `timeStepper Newton` -> `<frame> <alpha> <E> <|g|^2> 0`        (Optimizer::fullyImplicit, Optimizer.cpp:666-684)"""
+
+    def __init__(self, path: str, time_stepper: str = "DOT"):
         self.f = open(path, "w")
+        self.tail = " 0" if time_stepper == "Newton" else ""
 
     def frame(self, frame_index: int, log: np.ndarray) -> None:
         """log: rows (alpha, E, |g|^2) of one time step, row 0 = after initX (what Stepper.iter_log() returns)."""
         for a, E, gg in np.asarray(log).reshape(-1, 3):
-            self.f.write("%d %g %g %g 0\n" % (frame_index, a, E, gg))
+            self.f.write("%d %g %g %g%s\n" % (frame_index, a, E, gg, self.tail))
         self.f.flush()
 
     def close(self):

@@ -158,6 +158,38 @@ def gen_mesh(name, parts_list):
             shutil.rmtree(tmp, ignore_errors=True)
 
 
+def gen_io_fixture():
+    """tests/golden/io_small.npz: the files the REFERENCE writes for one short run - status<n> (Optimizer::saveStatus), iterStats.txt
+    (DOT and Newton flavours), the final .msh (IglUtils::saveTetMesh) - as raw text, next to the same state as binary arrays, so that
+    dot_b200/io.py's writers / readers can be compared with them byte for byte / field for field."""
+    out = {}
+    for stepper in ("DOT", "Newton"):
+        tmp = tempfile.mkdtemp(prefix="golden_")
+        try:
+            V, T, msh = make_mesh(tmp, "bar_tiny")
+            script = os.path.join(tmp, "s.txt")
+            meshgen.write_script(script, msh, energy="SNH", parts=4, anim="twist", stepper=stepper)
+            dd = os.path.join(tmp, "dump")
+            stats = run_ref(["--script", script, "--frames", "3", "--quiet", "--dump-dir", dd, "--dump-frames", "3", "--he-cap", "1", "--save-status",
+                             "--save-msh", os.path.join(tmp, "final.msh")], tmp)
+            of = os.path.join(tmp, stats["output_folder"])
+            key = stepper.lower()
+            out[key + "/iterStats_txt"] = np.array(open(os.path.join(of, "iterStats.txt")).read())
+            if stepper == "DOT":
+                n = stats["timestep"]
+                out["status_txt"] = np.array(open(os.path.join(of, "status%d" % n)).read())
+                out["status_timestep"] = np.array(n)
+                out["msh_txt"] = np.array(open(os.path.join(tmp, "final.msh")).read())
+                out["V"] = np.load(os.path.join(dd, "frame3", "V.npy"))
+                out["velocity"] = np.load(os.path.join(dd, "frame3", "velocity.npy"))
+                out["T"] = T.astype(np.int32)
+                out["SF"] = meshgen.surface_tris(T)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    np.savez_compressed(os.path.join(GOLD, "io_small.npz"), **out)
+    print("io_small ->", sorted(out))
+
+
 def gen_labels(preset, parts):
     """Labels only: run set-up (METIS + DD) and keep epart."""
     tmp = tempfile.mkdtemp(prefix="golden_")
@@ -179,6 +211,7 @@ def gen_labels(preset, parts):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--labels", action="store_true")
+    ap.add_argument("--io", action="store_true", help="files written by the reference (status, iterStats, .msh) as a fixture")
     ap.add_argument("--meshes", action="store_true", help="fixtures of the reference's own input meshes + their METIS labels")
     ap.add_argument("--only", default="")
     a = ap.parse_args()
@@ -197,6 +230,8 @@ if __name__ == "__main__":
     for c in KERNEL_CASES:
         if not a.only or a.only in c[0]:
             gen_kernel_case(*c)
+    if a.io:
+        gen_io_fixture()
     if a.meshes:
         for c in MESH_CASES:
             if not a.only or a.only in c[0]:

@@ -299,7 +299,8 @@ static void usage()
 
 int main(int argc, char** argv)
 {
-    std::string script, meshOverride, energy, stepper, anim, dumpDir, kernelState, statsJson, finalV;
+    std::string script, meshOverride, energy, stepper, anim, dumpDir, kernelState, statsJson, finalV, saveMsh;
+    bool saveStatus = false;
     bool fullPrecision = false;
     int parts = -1, frames = 10, threads = 0;
     long heCap = -1;
@@ -327,6 +328,8 @@ int main(int argc, char** argv)
         else if (a == "--he-cap") heCap = std::stol(next());
         else if (a == "--kernel-state") kernelState = next();
         else if (a == "--stats-json") statsJson = next();
+        else if (a == "--save-status") saveStatus = true;     // Optimizer::saveStatus() after the last frame -> <output folder>/status<n> (+ <n>.obj)
+        else if (a == "--save-msh") saveMsh = next();         // Mesh::saveAsMesh -> IglUtils::saveTetMesh of the final configuration
         else if (a == "--final-V") finalV = next();            // positions after the last frame, [nV,3] float64 .npy
         else if (a == "--full-precision") fullPrecision = true;  // iterStats.txt with 17 significant digits (default: the reference's 6)
         else if (a == "--dump-frames") { std::stringstream ss(next()); std::string t; while (std::getline(ss, t, ',')) dumpFrames.insert(std::stoi(t)); }
@@ -495,6 +498,8 @@ int main(int argc, char** argv)
     }
     const DOT::Mesh<DIM>& R = opt->getResult();
     double sumV = R.V.sum(), sqV = R.V.squaredNorm();
+    if (saveStatus) opt->saveStatus();
+    if (!saveMsh.empty()) DOT::IglUtils::saveTetMesh(saveMsh, R.V, R.F, SF, false);
     if (!finalV.empty()) {
         std::vector<double> rm((size_t)R.V.rows() * 3);
         for (long v = 0; v < R.V.rows(); ++v) for (int c = 0; c < 3; ++c) rm[v * 3 + c] = R.V(v, c);
@@ -507,7 +512,8 @@ int main(int argc, char** argv)
        << ", \"nT\": " << R.F.rows() << ", \"nV\": " << R.V.rows() << ", \"parts\": " << config.partitionAmt
        << ", \"energy\": \"" << DOT::Config::getStrByEnergyType(config.energyType) << "\""
        << ", \"sumV\": " << sumV << ", \"sqnormV\": " << sqV << ", \"line_search_halvings\": " << opt->numOfLineSearch
-       << ", \"targetGRes\": " << opt->targetGRes << ", \"iter_stats\": \"" << outputFolderPath << "iterStats.txt\"";
+       << ", \"targetGRes\": " << opt->targetGRes << ", \"iter_stats\": \"" << outputFolderPath << "iterStats.txt\""
+       << ", \"output_folder\": \"" << outputFolderPath << "\", \"timestep\": " << opt->globalIterNum;
     js << ", \"timers_sec\": {";
     for (int a = 0; a < 14; ++a) js << (a ? ", " : "") << "\"" << stepActs[a] << "\": " << timer_step.timing(a);
     js << "}, \"frame_sec\": [";

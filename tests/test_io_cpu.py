@@ -54,10 +54,14 @@ def test_msh_and_status_round_trip(tmp_path):
     assert st["timestep"] == 7
     assert np.allclose(st["position"], x, rtol=1e-6) and np.allclose(st["velocity"], v, rtol=1e-6)   # %le keeps 7 digits, like the reference
     assert st["dx_Elastic"].shape == x.shape
-    w = io.IterStatsWriter(str(tmp_path / "iterStats.txt"))
+    w = io.IterStatsWriter(str(tmp_path / "iterStats.txt"), "Newton")
     w.frame(0, np.array([[0.0, 1.5, 2.5], [1.0, 1.25, 1e-9]]))
     w.close()
     assert open(tmp_path / "iterStats.txt").read().splitlines() == ["0 0 1.5 2.5 0", "0 1 1.25 1e-09 0"]
+    w = io.IterStatsWriter(str(tmp_path / "iterStats_dot.txt"))
+    w.frame(0, np.array([[0.0, 1.5, 2.5], [1.0, 1.25, 1e-9]]))
+    w.close()
+    assert open(tmp_path / "iterStats_dot.txt").read().splitlines() == ["0 0 1.5 2.5", "0 1 1.25 1e-09"]
 
 
 def test_rotate_model_matches_axis_angle():
@@ -92,3 +96,63 @@ def test_reference_scripts_and_meshes_parse():
     assert (V.shape[0], T.shape[0]) == (4670, 19379) and SF.shape[0] > 0       # bunny5K sizes
     Dm = np.stack([V[T[:, 1]] - V[T[:, 0]], V[T[:, 2]] - V[T[:, 0]], V[T[:, 3]] - V[T[:, 0]]], axis=2)
     assert (np.linalg.det(Dm) > 0).all()
+
+
+def _io_fixture():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io_small.npz"))
+
+
+def test_status_file_is_byte_compatible_with_the_reference(tmp_path):
+    """SURVEY 8(f3): `status<n>` as Optimizer::saveStatus writes it (Optimizer.cpp:1096-1130; fixture written by the unmodified
+    reference, oracle/gen_golden.py --io).  Reading it gives the reference's state; writing that state back gives the same BYTES."""
+    z = _io_fixture()
+    ref_txt = str(z["status_txt"])
+    p = tmp_path / "status_ref"
+    p.write_text(ref_txt)
+    st = io.read_status(str(p))
+    assert st["timestep"] == int(z["status_timestep"])
+    # %le keeps 7 significant digits: the parsed fields are the reference's binary state to that precision
+    assert np.allclose(st["position"], z["V"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(st["velocity"], z["velocity"].reshape(-1), rtol=1e-6, atol=1e-12)
+    assert st["dx_Elastic"].shape == z["V"].shape
+    q = tmp_path / "status_mine"
+    io.write_status(str(q), st["timestep"], z["V"], z["velocity"], st["dx_Elastic"])   # positions / velocity from the BINARY state
+    assert q.read_text() == ref_txt
+
+
+def test_iterstats_rows_match_the_reference_format(tmp_path):
+    """iterStats.txt of `timeStepper DOT` has 4 columns, of `timeStepper Newton` a trailing ` 0`: re-writing the parsed
+    rows of the reference's own files reproduces them byte for byte (default ostream formatting == %g)."""
+    z = _io_fixture()
+    for kind, key in (("DOT", "dot/iterStats_txt"), ("Newton", "newton/iterStats_txt")):
+        ref_txt = str(z[key])
+        rows = np.array([[float(v) for v in line.split()] for line in ref_txt.strip().splitlines()])
+        assert rows.shape[1] == (4 if kind == "DOT" else 5)
+        p = tmp_path / ("iter_%s.txt" % kind)
+        w = io.IterStatsWriter(str(p), kind)
+        for f in np.unique(rows[:, 0]).astype(int):
+            w.frame(int(f), rows[rows[:, 0] == f][:, 1:4])
+        w.close()
+        assert p.read_text() == ref_txt
+
+
+def test_msh_writer_matches_saveTetMesh(tmp_path):
+    """.msh written by IglUtils::saveTetMesh (IglUtils.cpp:627-679) for the reference's final configuration vs
+    io.write_msh_reference for the same arrays: identical bytes; and the reader recovers the arrays from the reference's file."""
+    z = _io_fixture()
+    ref_txt = str(z["msh_txt"])
+    p = tmp_path / "ref.msh"
+    p.write_text(ref_txt)
+    V, T, SF = io.read_msh(str(p))
+    assert np.array_equal(T, z["T"]) and np.array_equal(SF, z["SF"])
+    assert np.allclose(V, z["V"], rtol=1e-6, atol=1e-12)
+    q = tmp_path / "mine.msh"
+    io.write_msh_reference(str(q), z["V"], z["T"], z["SF"])
+    assert q.read_text() == ref_txt
+
+
+def test_script_defaults_are_the_reference_defaults(tmp_path):
+    p = tmp_path / "s.txt"
+    p.write_text("energy FCR\n")
+    s = io.parse_script(str(p))
+    assert (s.rho, s.YM, s.PR, s.dt, s.duration, s.warm_start, s.handle_ratio) == (1.0, 100.0, 0.4, 0.025, 10.0, 2, 0.01)   # Config.cpp:33-37
