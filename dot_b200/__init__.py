@@ -7,4 +7,4 @@ DOTTimeStepper -> Stepper).  There is no CPU fallback: compute entry points rais
 CUDA device is visible, and importing the binding fails loudly if the library has not been built.
 """
 from .api import (ANIM_KINDS, ENERGY_FCR, ENERGY_SNH, Anim, DD, DotGpuError, Energy, FrameStats, Solver, Stepper,  # noqa: F401
-                  device_count, lib, lib_path, mesh_features, nccl_unique_id, owned_subdomains, partition, balanced_owner)
+                  device_count, lib, lib_path, mesh_features, nccl_unique_id, owned_subdomains, partition, partition_nodes, balanced_owner)

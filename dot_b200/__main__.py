@@ -46,8 +46,12 @@ def main(argv=None):
         sys.exit("warmStart %d is outside the GPU path: the resident stepper implements initX(2) (x^n + dt v^n + dt^2 g), Optimizer.cpp:472-493" % s.warm_start)
     if s.unknown:
         print("warning: script keys ignored by the GPU path: %s" % ", ".join(s.unknown), file=sys.stderr)
-    if newton:
+    node_part = None
+    if newton or s.time_stepper == "LBFGSH":
         k, epart = 1, np.zeros(T.shape[0], dtype=np.int32)
+    elif s.time_stepper == "LBFGSJH":
+        k, epart = s.partitions, np.zeros(T.shape[0], dtype=np.int32)
+        node_part = D.partition_nodes(V.shape[0], T, k)      # METIS<3>::partMesh_nodes (needs libdotmetis.so)
     else:
         k = s.partitions if s.block_size <= 0 else V.shape[0] // s.block_size + 1
         if a.labels:
@@ -68,7 +72,7 @@ def main(argv=None):
     gravity = (0.0, -9.80665, 0.0) if s.with_gravity else (0.0, 0.0, 0.0)
     t0 = time.time()
     stp = D.Stepper(V, T, epart, fixed, energy=s.energy, k=k, dt=s.dt, device=a.device, rel_tol=s.rel_tol(0), YM=s.YM, PR=s.PR, rho=s.rho,
-                    newton=newton, gravity=gravity)
+                    newton=newton, gravity=gravity, method=s.time_stepper, node_part=node_part)
     x = V.copy()
     frame0 = 0
     if s.restart:
@@ -79,7 +83,7 @@ def main(argv=None):
     setup = time.time() - t0
     os.makedirs(a.out, exist_ok=True)
     stats = io.IterStatsWriter(os.path.join(a.out, "iterStats.txt"), s.time_stepper)
-    if SF.shape[0] and not newton:
+    if SF.shape[0] and s.time_stepper == "DOT":
         io.write_label_obj(os.path.join(a.out, "label.obj"), SF, io.surface_to_tet(T, SF), epart)
     nframes = a.frames if a.frames is not None else s.num_frames() - frame0
     iters = 0

@@ -34,7 +34,7 @@ class StepperConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("energy_type", C.c_int32), ("num_subdomains", C.c_int32), ("history", C.c_int32),
                 ("dt", C.c_double), ("gravity", C.c_double * 3), ("rel_tol", C.c_double), ("YM", C.c_double), ("PR", C.c_double),
                 ("rho", C.c_double), ("max_iters", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("nccl_unique_id", C.c_void_p), ("target_fixed_count", C.c_int32), ("flags", C.c_int32)]
+                ("nccl_unique_id", C.c_void_p), ("target_fixed_count", C.c_int32), ("flags", C.c_int32), ("node_part", C.c_void_p)]
 
 
 class FrameStats(C.Structure):
@@ -120,6 +120,14 @@ def partition(nV, tets, k):
     ep = np.empty(T.shape[0], dtype=np.int32)
     _chk(lib().dotgpu_partition(int(nV), T.shape[0], _p(T), int(k), _p(ep)))
     return ep
+
+
+def partition_nodes(nV, tets, k):
+    """METIS<3>::partMesh_nodes (METIS_PartMeshNodal, the reference's vendored METIS and option vector): node labels [nV] int32."""
+    T = _i32(tets)
+    npart = np.empty(int(nV), dtype=np.int32)
+    _chk(lib().dotgpu_partition_nodes(int(nV), T.shape[0], _p(T), int(k), _p(npart)))
+    return npart
 
 
 def mesh_features(V_rest, tets, YM=1e5, PR=0.4, rho=1000.0):
@@ -318,9 +326,17 @@ class Stepper:
     (Optimizer::solve_oneStep, the reference's `timeStepper Newton`)."""
 
     def __init__(self, V_rest, tets, epart, fixed_mask, energy="SNH", k=None, dt=0.025, device=0, rel_tol=1e-5, YM=1e5, PR=0.4,
-                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000, newton=False, gravity=(0.0, -9.80665, 0.0)):
+                 rho=1000.0, history=5, rank=0, world=1, nccl_id: bytes | None = None, max_iters=10000, newton=False, gravity=(0.0, -9.80665, 0.0),
+                 method="DOT", node_part=None):
+        """method: "DOT" (default), "Newton" (= newton=True), "LBFGSH" (global Hessian initialiser, k = 1), "LBFGSJH" (block Jacobi over
+        the node partition `node_part`, k blocks) - the reference's `timeStepper` names."""
         V = _f64(V_rest)
         T = _i32(tets)
+        newton = newton or method == "Newton"
+        if method in ("LBFGSH", "LBFGSJH") or epart is None:
+            epart = np.zeros(T.shape[0], dtype=np.int32)
+        if method == "LBFGSH":
+            k = 1
         ep = _i32(epart)
         self.nV, self.nT = V.shape[0], T.shape[0]
         cfg = StepperConfig()
@@ -338,6 +354,15 @@ class Stepper:
             cfg.gravity[i] = float(gravity[i])
         if newton:
             cfg.flags |= 2  # DOTGPU_FLAG_NEWTON
+        if method == "LBFGSH":
+            cfg.flags |= 4  # DOTGPU_FLAG_LBFGS_H
+        self._npart = None
+        if method == "LBFGSJH":
+            cfg.flags |= 8  # DOTGPU_FLAG_LBFGS_JH
+            self._npart = _i32(node_part)
+            assert self._npart.shape[0] == self.nV
+            cfg.node_part = self._npart.ctypes.data_as(C.c_void_p)
+            cfg.num_subdomains = int(k if k is not None else self._npart.max() + 1)
         self._id = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         cfg.nccl_unique_id = C.cast(self._id, C.c_void_p) if self._id is not None else None
         self.cfg = cfg

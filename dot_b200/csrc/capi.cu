@@ -466,6 +466,7 @@ void dotgpu_stepper_default_config(dotgpu_stepper_config* c) {
     c->nccl_unique_id = nullptr;
     c->target_fixed_count = 1;
     c->flags = 0;
+    c->node_part = nullptr;
 }
 
 int dotgpu_nccl_unique_id(void* out128) {
@@ -606,6 +607,11 @@ int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out) {
     if (out)
         for (size_t i = 0; i < s->s.owned.size(); ++i) out[i] = s->s.owned[i];
     return (int)s->s.owned.size();
+}
+int dotgpu_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out) {
+    API_BEGIN
+    metis_partition_nodes(nV, nT, tets, k, npart_out);
+    API_END
 }
 int dotgpu_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out) {
     API_BEGIN

@@ -340,4 +340,97 @@ void DDHost::build(int nV_, int nT_, const int32_t* T, const int32_t* epart, int
     }
 }
 
+// SURVEY 8(f4), LBFGS-JH (LBFGSTimeStepper.cpp:60-92, 241-262, 318-331): block Jacobi of the global PD-projected Hessian over a NODE
+// partition.  Block s = the nodes with npart == s (ascending, METIS::getNodeList), its matrix = the global matrix restricted to those
+// nodes (LinSysSolver::getTriplets, LinSysSolver.hpp:256-284): EVERY tet incident to a block vertex contributes the 3x3 blocks between
+// vertices of the block, the lumped mass sits on the free diagonals, fixed vertices are identity rows.  Expressed with the same ordered
+// gather lists as the subdomain matrices, so fill / factorisation / solves / scatter run unchanged (dup == 1 everywhere).
+void DDHost::build_node_blocks(int nV_, int nT_, const int32_t* T, const int32_t* npart, int k_, const uint8_t* fixed_mask,
+                               const double* mass_global) {
+    nV = nV_;
+    nT = nT_;
+    k = k_;
+    if (k < 1) throw std::invalid_argument("k < 1");
+    for (int v = 0; v < nV; ++v)
+        if (npart[v] < 0 || npart[v] >= k) throw std::invalid_argument("node label out of range");
+    std::vector<uint8_t> fixed(nV, 0);
+    if (fixed_mask) fixed.assign(fixed_mask, fixed_mask + nV);
+    std::vector<int> vfp(nV + 1, 0), vfi((size_t)4 * nT);
+    for (size_t i = 0; i < (size_t)4 * nT; ++i) vfp[T[i] + 1]++;
+    for (int v = 0; v < nV; ++v) vfp[v + 1] += vfp[v];
+    {
+        std::vector<int> cur(vfp.begin(), vfp.end() - 1);
+        for (int t = 0; t < nT; ++t)
+            for (int c = 0; c < 4; ++c) vfi[cur[T[4 * t + c]]++] = 4 * t + c;
+    }
+    std::vector<int> gap, gai;
+    vertex_adjacency(nV, nT, T, gap, gai);
+    build_pattern(nV, gap, gai, fixed, gpat);
+    ListBuilder lb;
+    // global matrix (the SpMV of initStepSize is not used by LBFGS-JH, but the checkers read it)
+    gfill.ptr.assign(1, 0);
+    gfill.src.clear();
+    gfill.consts.assign(1, 1.0);
+    for (int v = 0; v < nV; ++v) gfill.consts.push_back(mass_global ? mass_global[v] : 0.0);
+    auto fill_rows = [&](const MatrixPattern& P, FillList& f, const std::vector<int32_t>& l2g, const std::vector<int>& g2l) {
+        for (int lv = 0; lv < P.nverts; ++lv) {
+            const int g = l2g[lv];
+            lb.start((size_t)(P.bptr[lv + 1] - P.bptr[lv]));
+            if (fixed[g]) {
+                lb.rows[0].push_back(-1);  // identity (IglUtils.hpp:148-157)
+            } else {
+                for (int i = vfp[g]; i < vfp[g + 1]; ++i) {
+                    const int t = vfi[i] >> 2, a = vfi[i] & 3;
+                    for (int b = 0; b < 4; ++b) {
+                        const int w = T[4 * (size_t)t + b];
+                        const int lu = g2l[w];
+                        if (fixed[w] || lu < lv) continue;     // lu < 0: outside the block
+                        const int blk = find_block(P, lv, lu);
+                        lb.rows[blk - P.bptr[lv]].push_back(16 * t + 4 * a + b);
+                    }
+                }
+                lb.rows[0].push_back(-(1 + lv) - 1);  // + m_v
+            }
+            lb.flush(f);
+        }
+    };
+    {
+        std::vector<int32_t> ident(nV);
+        std::vector<int> g2l(nV);
+        for (int v = 0; v < nV; ++v) ident[v] = g2l[v] = v;
+        fill_rows(gpat, gfill, ident, g2l);
+    }
+    subs.assign(k, SubdomainHost());
+    dup.assign(nV, 1);
+    for (int v = 0; v < nV; ++v) subs[npart[v]].l2g.push_back(v);  // ascending node ids
+    std::vector<int> g2l(nV, -1);
+    for (int s = 0; s < k; ++s) {
+        SubdomainHost& sd = subs[s];
+        const int nl = (int)sd.l2g.size();
+        if (nl == 0) throw std::invalid_argument("empty node block");
+        for (int l = 0; l < nl; ++l) g2l[sd.l2g[l]] = l;
+        std::vector<uint8_t> fl(nl, 0);
+        sd.mass_local.assign(nl, 0.0);
+        for (int l = 0; l < nl; ++l) {
+            fl[l] = fixed[sd.l2g[l]];
+            if (fl[l]) sd.fixed_local.push_back(l);
+            sd.mass_local[l] = mass_global ? mass_global[sd.l2g[l]] : 0.0;
+        }
+        std::vector<int> lap(nl + 1, 0), lai;
+        for (int l = 0; l < nl; ++l) {
+            const int g = sd.l2g[l];
+            for (int i = gap[g]; i < gap[g + 1]; ++i)
+                if (g2l[gai[i]] >= 0) lai.push_back(g2l[gai[i]]);  // ascending: l2g is ascending
+            lap[l + 1] = (int)lai.size();
+        }
+        build_pattern(nl, lap, lai, fl, sd.pat);
+        sd.fill.ptr.assign(1, 0);
+        sd.fill.src.clear();
+        sd.fill.consts.assign(1, 1.0);
+        for (int l = 0; l < nl; ++l) sd.fill.consts.push_back(sd.mass_local[l]);
+        fill_rows(sd.pat, sd.fill, sd.l2g, g2l);
+        for (int l = 0; l < nl; ++l) g2l[sd.l2g[l]] = -1;
+    }
+}
+
 }  // namespace dotgpu

@@ -62,9 +62,14 @@ struct DDHost {
     // V_rest/rho may be null/0 when only the combinatorial part is wanted (labels, patterns)
     void build(int nV, int nT, const int32_t* tets, const int32_t* epart, int k, const uint8_t* fixed_mask,
                const double* V_rest, double rho, const double* mass_global, bool with_fill, const std::vector<char>* sub_mask = nullptr);
+    // LBFGS-JH: node blocks instead of element subdomains (block Jacobi of the global Hessian, LBFGSTimeStepper.cpp:241-262)
+    void build_node_blocks(int nV, int nT, const int32_t* tets, const int32_t* npart, int k, const uint8_t* fixed_mask,
+                           const double* mass_global);
 };
 
 // a14: element labels from the reference's vendored METIS (partition_host.cpp; dlopen of libdotmetis.so)
 void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out);
+// METIS<3>::partMesh_nodes (METIS_PartMeshNodal with the same option vector, Utils/METIS.hpp:161-212): node labels [nV]
+void metis_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out);
 
 }  // namespace dotgpu

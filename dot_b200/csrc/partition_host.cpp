@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.h"
+#include "mesh_host.h"
 
 namespace dotgpu {
 namespace {
@@ -29,11 +30,13 @@ constexpr int kMetisOK = 1;
 
 typedef int (*fn_defaults)(idx_t*);
 typedef int (*fn_partmeshdual)(idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, real_t*, idx_t*, idx_t*, idx_t*, idx_t*);
+typedef int (*fn_partmeshnodal)(idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, real_t*, idx_t*, idx_t*, idx_t*, idx_t*);
 
 struct MetisLib {
     void* h = nullptr;
     fn_defaults defaults = nullptr;
     fn_partmeshdual part = nullptr;
+    fn_partmeshnodal part_nodal = nullptr;
     std::string err;
 };
 
@@ -58,6 +61,7 @@ MetisLib& metis() {
         if (!L.h) return;
         L.defaults = (fn_defaults)dlsym(L.h, "METIS_SetDefaultOptions");
         L.part = (fn_partmeshdual)dlsym(L.h, "METIS_PartMeshDual");
+        L.part_nodal = (fn_partmeshnodal)dlsym(L.h, "METIS_PartMeshNodal");
         if (!L.defaults || !L.part) L.err = "libdotmetis.so lacks METIS_SetDefaultOptions / METIS_PartMeshDual";
     });
     return L;
@@ -65,11 +69,11 @@ MetisLib& metis() {
 
 }  // namespace
 
-void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out) {
-    DG_REQUIRE(nV > 0 && nT > 0 && tets && epart_out, "null or empty mesh");
+static void metis_part(int nV, int nT, const int32_t* tets, int k, bool nodal, int32_t* out) {
+    DG_REQUIRE(nV > 0 && nT > 0 && tets && out, "null or empty mesh");
     DG_REQUIRE(k >= 2, "the number of partitions must be at least 2 (METIS.hpp:300-302)");
     MetisLib& L = metis();
-    if (!L.h || !L.defaults || !L.part)
+    if (!L.h || !L.defaults || !L.part || !L.part_nodal)
         throw Error(DOTGPU_ERR_STATE, "libdotmetis.so (the reference's vendored METIS 5.1.0, built by dot_b200/build.py) is not available: " + L.err +
                                           "; pass labels produced elsewhere instead");
     // mesh in METIS' element-node form (METIS.hpp:89-105)
@@ -95,13 +99,19 @@ void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_
     options[OPT_SEED] = -1;    // -> 4321 inside METIS (libmetis/util.c:23)
     options[OPT_UFACTOR] = 30;
     idx_t ne = nT, nn = nV, ncommon = 3, nparts = k, objval = 0;
-    std::vector<idx_t> ewgt((size_t)nT, 1), epart((size_t)nT), npart((size_t)nV);
-    std::vector<real_t> tpwgts((size_t)k, 1.0f / k);   // real_t(1.0 / nparts) per part, as std::vector<real_t>(nparts, 1.0 / nparts)
-    for (auto& w : tpwgts) w = (real_t)(1.0 / k);
-    int status = L.part(&ne, &nn, eptr.data(), eind.data(), ewgt.data(), nullptr, &ncommon, &nparts, tpwgts.data(), options, &objval,
-                        epart.data(), npart.data());
-    if (status != kMetisOK) throw Error(DOTGPU_ERR_INVALID, "METIS_PartMeshDual failed with status " + std::to_string(status));
-    for (int t = 0; t < nT; ++t) epart_out[t] = (int32_t)epart[t];
+    std::vector<idx_t> wgt((size_t)(nodal ? nV : nT), 1), epart((size_t)nT), npart((size_t)nV);
+    std::vector<real_t> tpwgts((size_t)k);
+    for (auto& w : tpwgts) w = (real_t)(1.0 / k);   // std::vector<real_t>(nparts, 1.0 / nparts)
+    const int status = nodal ? L.part_nodal(&ne, &nn, eptr.data(), eind.data(), wgt.data(), nullptr, &nparts, tpwgts.data(), options, &objval,
+                                            epart.data(), npart.data())
+                             : L.part(&ne, &nn, eptr.data(), eind.data(), wgt.data(), nullptr, &ncommon, &nparts, tpwgts.data(), options, &objval,
+                                      epart.data(), npart.data());
+    if (status != kMetisOK) throw Error(DOTGPU_ERR_INVALID, "METIS failed with status " + std::to_string(status));
+    if (nodal) for (int v = 0; v < nV; ++v) out[v] = (int32_t)npart[v];
+    else for (int t = 0; t < nT; ++t) out[t] = (int32_t)epart[t];
 }
+
+void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out) { metis_part(nV, nT, tets, k, false, epart_out); }
+void metis_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out) { metis_part(nV, nT, tets, k, true, npart_out); }
 
 }  // namespace dotgpu

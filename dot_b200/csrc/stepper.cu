@@ -129,7 +129,8 @@ void Stepper::setup_decomposition() {
     for (int s = 0; s < k; ++s)
         if (owner[s] == cfg.rank) owned.push_back(s);
     for (int s : owned) mask[s] = 1;
-    dd.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), V_rest.data(), cfg.rho, mass_h.data(), true, &mask);
+    if (lbfgs_jh) dd.build_node_blocks(nV, nT, tets_h.data(), npart_h.data(), k, fixed_h.data(), mass_h.data());
+    else dd.build(nV, nT, tets_h.data(), epart_h.data(), k, fixed_h.data(), V_rest.data(), cfg.rho, mass_h.data(), true, &mask);
     if (cfg.world > 1 && mesh_own.nT == 0) {
         // energy / gradient are sharded by tet: this rank evaluates the tets of its own subdomains (the element partition is
         // disjoint, DOTTimeStepper.cpp:406-450 / SURVEY 8(e)); the sums over the ranks are one all-reduce per evaluation
@@ -247,7 +248,8 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     cfg = c;
     nV = nV_;
     nT = nT_;
-    DG_REQUIRE(nV > 0 && nT > 0 && Vr && T && ep, "null or empty mesh");
+    DG_REQUIRE(nV > 0 && nT > 0 && Vr && T, "null or empty mesh");
+    DG_REQUIRE(ep || (c.flags & (DOTGPU_FLAG_LBFGS_H | DOTGPU_FLAG_LBFGS_JH | DOTGPU_FLAG_NEWTON)), "element labels missing");
     // history + 1 (S, Y) buffers are in use (the candidate pair lives in a spare slot), and the device scalar table has
     // LB_MAXH slots per row (linalg.h) -> at most LB_MAXH - 1 pairs
     static_assert(SC_YP - SC_SG == LB_MAXH && SC_XI - SC_YP == LB_MAXH && SC_SY - SC_XI == LB_MAXH && SC_COUNT == SC_SY + LB_MAXH * LB_MAXH,
@@ -261,6 +263,12 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
         DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "Projected Newton runs on one subdomain (the whole mesh) and one GPU");
         cfg.history = 0;  // no quasi-Newton pairs: p = -H(x)^-1 g with the Hessian at the current iterate
     }
+    lbfgs_h = (cfg.flags & DOTGPU_FLAG_LBFGS_H) != 0;
+    lbfgs_jh = (cfg.flags & DOTGPU_FLAG_LBFGS_JH) != 0;
+    DG_REQUIRE((int)newton + (int)lbfgs_h + (int)lbfgs_jh <= 1, "DOTGPU_FLAG_NEWTON / LBFGS_H / LBFGS_JH exclude each other");
+    if (lbfgs_h) DG_REQUIRE(cfg.num_subdomains == 1 && cfg.world == 1, "LBFGS-H factorises ONE global matrix: num_subdomains = 1, one GPU");
+    if (lbfgs_jh) DG_REQUIRE(cfg.node_part != nullptr && cfg.num_subdomains >= 2 && cfg.world == 1, "LBFGS-JH needs node labels, k >= 2, one GPU");
+    unit_step = newton || lbfgs_h || lbfgs_jh;  // Optimizer::initStepSize: only TST_DOT starts from -p.g / p.Hp (Optimizer.cpp:1076-1093)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(DOTGPU_ERR_NO_DEVICE, "no CUDA device");
     DG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device index out of range");
@@ -270,7 +278,12 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     launches0 = g_launch_count;
     V_rest.assign(Vr, Vr + 3 * (size_t)nV);
     tets_h.assign(T, T + 4 * (size_t)nT);
-    epart_h.assign(ep, ep + nT);
+    if (ep && !(c.flags & (DOTGPU_FLAG_LBFGS_H | DOTGPU_FLAG_LBFGS_JH))) epart_h.assign(ep, ep + nT);
+    else epart_h.assign(nT, 0);   // one "subdomain" = the whole mesh (LBFGS-H, Newton); unused by LBFGS-JH
+    if (c.flags & DOTGPU_FLAG_LBFGS_JH) {
+        DG_REQUIRE(c.node_part != nullptr, "LBFGS-JH needs node labels");
+        npart_h.assign(c.node_part, c.node_part + nV);
+    }
     fixed_h.assign(nV, 0);
     if (fixed_mask) fixed_h.assign(fixed_mask, fixed_mask + nV);
 
@@ -478,8 +491,8 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         }
         launch_lbfgs_p(n, p.p, H, sc.p, st);
         // ---- initial step length (Optimizer.cpp:1076-1093), computed and consumed on the device ----
-        const double* alpha_dev = newton ? nullptr : sc.p + SC_ALPHA;  // Newton: initStepSize = 1 (Optimizer.cpp:1088)
-        if (!newton) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
+        const double* alpha_dev = unit_step ? nullptr : sc.p + SC_ALPHA;  // everything but DOT: initStepSize = 1 (Optimizer.cpp:1088)
+        if (!unit_step) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st);
         // ---- back-tracking line search (Optimizer.cpp:752-881): the first trial and everything that follows an accepted
         //      step are enqueued without waiting; the host looks at the result once per iteration ----
         std::swap(x.p, x0.p);  // x0 = current positions
@@ -504,7 +517,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         };
         grad_pair(alpha_dev, 1.0, true);
         fetch_scalars(0, SC_COUNT);  // the one host round trip of an iteration (measured: ~14 us of 240 on bar17K_like)
-        double alpha = newton ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
+        double alpha = unit_step ? 1.0 : h_sc[SC_ALPHA], Et = h_sc[SC_E];
         // tests only (DOTGPU_DEBUG_LS_FAIL=1): every trial energy reads as +inf, so the step halves until it underflows.  (With real
         // energies that branch is nearly unreachable: x0 + alpha p rounds to x0 long before alpha reaches 0, and E(x0) > E(x0) is false.)
         if (debug_ls_fail) Et = INFINITY;

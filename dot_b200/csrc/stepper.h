@@ -59,6 +59,8 @@ struct Stepper {
     double* h_x = nullptr;           // pinned staging for positions
     double target = 0.0, target_per_tolsq = 0.0;
     bool newton = false;             // DOTGPU_FLAG_NEWTON
+    bool lbfgs_h = false, lbfgs_jh = false, unit_step = false;  // DOTGPU_FLAG_LBFGS_H / _JH; initStepSize = 1 (everything but DOT)
+    std::vector<int32_t> npart_h;    // LBFGS-JH node labels
     bool debug_ls_fail = false;      // tests only: every trial energy reads as +inf (exercises the failed-line-search exit)
     double E_last = 0.0;
     std::vector<double> iter_log;    // (alpha, E, |g|^2) rows

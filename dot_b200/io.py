@@ -29,7 +29,7 @@ ANIM_SCRIPTS = {"null": "null", "stretch": "stretch", "squash": "squash", "stret
 @dataclass
 class Script:
     energy: str = "FCR"
-    time_stepper: str = "Newton"      # "Newton" (Projected Newton) or "DOT"
+    time_stepper: str = "Newton"      # "Newton" (Projected Newton), "DOT", "LBFGSH" or "LBFGSJH"
     partitions: int = 4               # `timeStepper DOT k`; k < 2 is rewritten to 4 like Config.cpp:76-80
     block_size: int = -1              # `timeStepper DOT -1 <blockSize>`: k = nV / blockSize + 1 (main.cpp:792-798)
     size: float = 1.0                 # longest bounding-box edge after loading (main.cpp:709)
@@ -77,15 +77,15 @@ def parse_script(path: str) -> Script:
             s.energy = args[0]
         elif key == "timeStepper":
             s.time_stepper = args[0]
-            if args[0] == "DOT":
+            if args[0] in ("DOT", "LBFGSJH"):
                 k = int(args[1]) if len(args) > 1 else 4
                 if k < 0:
                     s.block_size = int(args[2])
                 elif k < 2:
                     k = 4
                 s.partitions = k
-            elif args[0] != "Newton":
-                raise ValueError("timeStepper %r is outside the GPU path (DOT and Newton are supported)" % args[0])
+            elif args[0] not in ("Newton", "LBFGSH"):
+                raise ValueError("timeStepper %r is outside the GPU path (DOT, Newton, LBFGSH and LBFGSJH are supported)" % args[0])
         elif key == "size":
             s.size = float(args[0])
         elif key == "time":

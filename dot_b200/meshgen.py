@@ -97,7 +97,8 @@ def write_script(path: str, msh_path: str, energy: str = "SNH", parts: int = 8, 
                  youngs: float = 1e5, poisson: float = 0.4, tol: float | None = None, stepper: str = "DOT") -> None:
     """A DOT script with the keys the shipped input/*.txt scripts use (reference Config.cpp:43-200)."""
     with open(path, "w") as f:
-        ts = "DOT %d" % parts if stepper == "DOT" else stepper  # `timeStepper Newton` = Projected Newton (Config.cpp:76-80)
+        # `timeStepper Newton` = Projected Newton; DOT and LBFGSJH take the partition count (Config.cpp:60-80)
+        ts = "%s %d" % (stepper, parts) if stepper in ("DOT", "LBFGSJH") else stepper
         f.write("energy %s\ntimeStepper %s\ninexactSolve 0\nwarmStart 2\nresolution 1000\nsize 1\n" % (energy, ts))
         f.write("time %.17g %.17g\ndensity %.17g\nstiffness %.17g %.17g\nscript %s\n" % (duration, dt, density, youngs, poisson, anim))
         f.write("shape input %s\n" % msh_path)

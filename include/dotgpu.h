@@ -133,6 +133,8 @@ typedef struct dotgpu_dd dotgpu_dd;
  * under the reference tree; 64-bit idx_t, 32-bit real_t).  epart_out [nT] = subdomain label per tet, bit-exact with the reference's.
  * Returns DOTGPU_ERR_STATE when libdotmetis.so is not available (then pass labels produced elsewhere to the calls below). */
 int dotgpu_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out);
+/* METIS<3>::partMesh_nodes (Utils/METIS.hpp:161-212: METIS_PartMeshNodal, same option vector; LBFGSTimeStepper.cpp:71-74): npart_out [nV] */
+int dotgpu_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out);
 int dotgpu_dd_create(dotgpu_dd** out, int nV, int nT, const int32_t* tets, const int32_t* epart, int k,
                      const uint8_t* fixed_mask);
 void dotgpu_dd_destroy(dotgpu_dd* d);
@@ -167,6 +169,13 @@ typedef struct dotgpu_stepper dotgpu_stepper;
                               * :1076-1093); `timeStepper Newton` scripts, the reference's "1 subdomain" case.  Use num_subdomains = 1,
                               * epart all 0. */
 
+/* the other L-BFGS initialisers of the reference that share the kernels (TimeStepper/LBFGSTimeStepper.cpp:108-265, 286-335,
+ * 339-420): same two-loop recursion and history, line search from step 1 (Optimizer::initStepSize uses p.Hp for DOT only), the initial
+ * inverse Hessian refreshed once per time step like DOT's. */
+#define DOTGPU_FLAG_LBFGS_H 4  /* `timeStepper LBFGSH` (D0T_H): the global PD-projected Hessian, one factorisation; num_subdomains = 1, epart ignored */
+#define DOTGPU_FLAG_LBFGS_JH 8 /* `timeStepper LBFGSJH k` (D0T_JH): block Jacobi of that matrix over the NODE partition config.node_part
+                                * (METIS<3>::partMesh_nodes = dotgpu_partition_nodes); num_subdomains = k, epart ignored */
+
 typedef struct dotgpu_stepper_config {
     int32_t device;
     int32_t energy_type;      /* DOTGPU_ENERGY_* */
@@ -181,6 +190,7 @@ typedef struct dotgpu_stepper_config {
     const void* nccl_unique_id; /* ncclUniqueId bytes (128) when world>1, else NULL */
     int32_t target_fixed_count; /* #fixed verts in the tolerance formula; reference uses 1 */
     int32_t flags;            /* DOTGPU_FLAG_* */
+    const int32_t* node_part; /* DOTGPU_FLAG_LBFGS_JH: node labels [nV] in [0, num_subdomains); else NULL */
 } dotgpu_stepper_config;
 void dotgpu_stepper_default_config(dotgpu_stepper_config* c);
 /* Round-robin map of subdomains to ranks (bookkeeping / DOTGPU_BALANCE=0; see dotgpu_balanced_owner and

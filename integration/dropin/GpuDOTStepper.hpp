@@ -82,17 +82,27 @@ public:
         dotgpu_stepper_config c;
         dotgpu_stepper_default_config(&c);
         const bool newton = Base::animConfig.timeStepperType == TST_NEWTON;
+        const bool lbfgsh = Base::animConfig.timeStepperType == TST_LBFGSH, lbfgsjh = Base::animConfig.timeStepperType == TST_LBFGSJH;
         c.energy_type = Base::animConfig.energyType == ET_SNH ? DOTGPU_ENERGY_SNH : DOTGPU_ENERGY_FCR;
-        c.num_subdomains = newton ? 1 : Base::animConfig.partitionAmt;
+        c.num_subdomains = (newton || lbfgsh) ? 1 : Base::animConfig.partitionAmt;
         c.dt = Base::dt;
         for (int i = 0; i < 3; ++i) c.gravity[i] = Base::gravity[i];
         c.YM = Base::animConfig.YM;
         c.PR = Base::animConfig.PR;
         c.rho = Base::animConfig.rho;
         if (newton) c.flags |= DOTGPU_FLAG_NEWTON;
+        if (lbfgsh) c.flags |= DOTGPU_FLAG_LBFGS_H;      // LBFGSTimeStepper D0T_H / D0T_JH on the same kernels
         epart.assign(nT, 0);
-        if (!newton)   // METIS<3>::partMesh with the reference's vendored METIS and option vector (Utils/METIS.hpp:109-160, 265-321)
+        std::vector<int32_t> npart;
+        if (lbfgsjh) {
+            c.flags |= DOTGPU_FLAG_LBFGS_JH;
+            npart.resize(nV);
+            check(dotgpu_partition_nodes(nV, nT, tets.data(), c.num_subdomains, npart.data()), "partition_nodes");
+            c.node_part = npart.data();
+        } else if (!newton && !lbfgsh) {
+            // METIS<3>::partMesh with the reference's vendored METIS and option vector (Utils/METIS.hpp:109-160, 265-321)
             check(dotgpu_partition(nV, nT, tets.data(), c.num_subdomains, epart.data()), "partition");
+        }
         maskFromResult();
         packV(M.V_rest);
         check(dotgpu_stepper_create(&h, &c, nV, nT, xbuf.data(), tets.data(), epart.data(), fixedMask.data()), "stepper_create");

@@ -772,6 +772,10 @@ class DOTStepper:
     def energy_at(self, x):
         return incremental_potential(self.energy, self.mesh, x, self.xTilde, self.dt)
 
+    def init_step(self, p, g):                                           # Optimizer::initStepSize, DOT branch (Optimizer.cpp:1076-1093)
+        Hp = spmv_sym(self.gia, self.gja, self.ga, p)
+        return max(0.1, min(1.0, -(p @ g) / (p @ Hp)))
+
     def step_frame(self):
         mesh, dt = self.mesh, self.dt
         self.x = self.anim.step(self.x, dt)                              # Optimizer.cpp:334
@@ -792,8 +796,7 @@ class DOTStepper:
             p = self.precondition(q)
             for i in range(len(dx)):
                 p = p + dx[i] * (ksi[i] - dg[i] @ p / dgdx[i])
-            Hp = spmv_sym(self.gia, self.gja, self.ga, p)
-            alpha = max(0.1, min(1.0, -(p @ g) / (p @ Hp)))              # Optimizer.cpp:1076-1093
+            alpha = self.init_step(p, g)
             x0 = self.x
             while True:
                 xt = x0 + alpha * p.reshape(-1, 3)
@@ -822,6 +825,43 @@ class DOTStepper:
         self.x_n = self.x.copy()
         self.compute_xtilde()
         return it
+
+
+# ---------------------------------------------------------------------------------------
+# f4  the other L-BFGS initialisers that share the kernels (LBFGSTimeStepper.cpp:108-265 precompute, 286-335 per-frame refresh,
+#     339-420 solve_oneStep): same two-loop recursion, history 5, line search from step 1 (initStepSize: only DOT uses p.Hp)
+# ---------------------------------------------------------------------------------------
+class LBFGSStepper(DOTStepper):
+    """d0 = "H": initial inverse Hessian = the global PD-projected Hessian (+ mass) at the start of the time step, factorised once
+    per frame (D0T_H).  d0 = "JH": block Jacobi of that matrix over a node partition (D0T_JH; `npart` = METIS<3>::partMesh_nodes
+    labels, node lists ascending): every block is solved on its own, results are scattered without averaging."""
+
+    def __init__(self, mesh, energy, d0="H", npart=None, anim_kind="twist", dt=0.025, handle_ratio=0.01, rel_tol=1e-5, history=5):
+        self.d0, self.npart = d0, None if npart is None else np.asarray(npart)
+        super().__init__(mesh, energy, np.zeros(mesh.nT, dtype=np.int64), anim_kind, dt, handle_ratio, rel_tol, history)
+
+    def refresh(self, svd):
+        F, U, s, V = svd
+        self.He = elem_hessians(self.energy, self.mesh, U, s, V, self.dt ** 2, True)
+        self.ga = fill_global(self.mesh, self.He, self.gia, self.gja, self.fixed_mask)      # Optimizer::computePrecondMtr
+        A = csr_upper_to_full(self.gia, self.gja, self.ga).tocsc()
+        if self.d0 == "H":
+            self.blocks = [(np.arange(3 * self.mesh.nV), spla.splu(A))]
+        else:
+            self.blocks = []
+            for b in range(int(self.npart.max()) + 1):
+                nodes = np.nonzero(self.npart == b)[0]
+                dof = (3 * nodes[:, None] + np.arange(3)[None, :]).ravel()
+                self.blocks.append((dof, spla.splu(A[dof][:, dof].tocsc())))
+
+    def precondition(self, q):
+        p = np.zeros_like(q)
+        for dof, lu in self.blocks:
+            p[dof] = lu.solve(q[dof])
+        return p
+
+    def init_step(self, p, g):
+        return 1.0
 
 
 # ---------------------------------------------------------------------------------------

@@ -55,6 +55,12 @@ PN_CASES = [
     ("small_fcr_newton_twist", "bar_small", "FCR", 4, "twist", 4, [1, 4], 16, 0.025),
     ("tiny_snh_newton_tsns", "bar_tiny", "SNH", 4, "twistnsns", 5, [1, 5], -1, 0.025),
 ]
+# the L-BFGS initialisers that share the kernels - LBFGS-H (global projected Hessian of the start of the time step) and
+# LBFGS-JH (block Jacobi of it over a METIS node partition), LBFGSTimeStepper.cpp:108-265, 339-420; 17-digit iterStats
+LBFGS_CASES = [
+    ("small_snh_lbfgsh_twist", "bar_small", "SNH", 4, "twist", 5, [1, 5], 16, 0.025, "LBFGSH"),
+    ("small_fcr_lbfgsjh4_tsns", "bar_small", "FCR", 4, "twistnsns", 5, [1, 5], 16, 0.025, "LBFGSJH"),
+]
 # kernel-level states: name, mesh, energy, parts, perturbation amplitude (x cell size), seed
 KERNEL_CASES = [
     ("tiny_fcr_inverted", "bar_tiny", "FCR", 4, 0.45, 12345),
@@ -92,11 +98,11 @@ def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepp
     try:
         V, T, msh = make_mesh(tmp, preset)
         script = os.path.join(tmp, "s.txt")
-        meshgen.write_script(script, msh, energy=energy, parts=parts, anim=anim, dt=dt)
+        meshgen.write_script(script, msh, energy=energy, parts=parts, anim=anim, dt=dt, stepper=stepper if stepper.startswith("LBFGS") else "DOT")
         dd = os.path.join(tmp, "dump")
         args = ["--script", script, "--frames", str(frames), "--quiet", "--dump-dir", dd,
                 "--dump-frames", ",".join(map(str, dumps)), "--he-cap", str(he_cap)]
-        if stepper != "DOT":
+        if stepper == "Newton":
             args += ["--stepper", stepper]
         if full_precision:
             args += ["--full-precision"]
@@ -224,6 +230,9 @@ if __name__ == "__main__":
     for c in HALVING_CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c, full_precision=True)
+    for c in LBFGS_CASES:
+        if not a.only or a.only in c[0]:
+            gen_case(*c[:9], stepper=c[9], full_precision=True)
     for c in PN_CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c, stepper="Newton")

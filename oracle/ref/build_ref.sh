@@ -73,7 +73,7 @@ dot_cc() {
 export -f dot_cc; export INC CXXF
 printf '%s\n' "$S/Energy/Energy.cpp" "$S/Energy/Physics_Elasticity/FixedCoRotEnergy.cpp" "$S/Energy/Physics_Elasticity/StableNHEnergy.cpp" \
   "$S/Mesh.cpp" "$S/Config.cpp" "$S/AnimScripter.cpp" "$S/Utils/IglUtils.cpp" "$S/LinSysSolver/CHOLMODSolver.cpp" \
-  "$S/TimeStepper/Optimizer.cpp" "$S/TimeStepper/ADMMDDTimeStepper.cpp" "$S/TimeStepper/DOTTimeStepper.cpp" \
+  "$S/TimeStepper/Optimizer.cpp" "$S/TimeStepper/ADMMDDTimeStepper.cpp" "$S/TimeStepper/DOTTimeStepper.cpp" "$S/TimeStepper/LBFGSTimeStepper.cpp" \
   "$S/Utils/SVD_EFTYCHIOS/Singular_Value_Decomposition_Helper.cpp" "$S/Utils/SVD_EFTYCHIOS/PTHREAD_QUEUE.cpp" \
   "$HERE/driver.cpp" | xargs -P "$JOBS" -I{} bash -c 'dot_cc {}'
 
@@ -96,7 +96,7 @@ if [ -f "$REPO/dot_b200/libdotgpu.so" ]; then
   export -f dotgpu_cc; export GINC REPO
   printf '%s\n' "$S/Energy/Energy.cpp" "$S/Energy/Physics_Elasticity/FixedCoRotEnergy.cpp" "$S/Energy/Physics_Elasticity/StableNHEnergy.cpp" \
     "$S/Mesh.cpp" "$S/Config.cpp" "$S/AnimScripter.cpp" "$S/Utils/IglUtils.cpp" \
-    "$S/TimeStepper/Optimizer.cpp" "$S/TimeStepper/ADMMDDTimeStepper.cpp" "$S/TimeStepper/DOTTimeStepper.cpp" \
+    "$S/TimeStepper/Optimizer.cpp" "$S/TimeStepper/ADMMDDTimeStepper.cpp" "$S/TimeStepper/DOTTimeStepper.cpp" "$S/TimeStepper/LBFGSTimeStepper.cpp" \
     "$S/Utils/SVD_EFTYCHIOS/Singular_Value_Decomposition_Helper.cpp" "$S/Utils/SVD_EFTYCHIOS/PTHREAD_QUEUE.cpp" \
     "$HERE/driver.cpp" | xargs -P "$JOBS" -I{} bash -c 'dotgpu_cc {}'
   g++ -fopenmp "$OBJ"/dot_gpu/*.o "$OUT/libmetis.a" -L"$REPO/dot_b200" -ldotgpu -Wl,--disable-new-dtags \

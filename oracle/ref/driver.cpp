@@ -38,6 +38,7 @@
 #include "Optimizer.hpp"
 #include "ADMMDDTimeStepper.hpp"
 #include "DOTTimeStepper.hpp"
+#include "LBFGSTimeStepper.hpp"
 #include "FixedCoRotEnergy.hpp"
 #include "StableNHEnergy.hpp"
 #include "METIS.hpp"
@@ -450,7 +451,20 @@ int main(int argc, char** argv)
     switch (config.timeStepperType) {
         case DOT::TST_NEWTON: opt = new Opt(*temp, energyTerms, energyParams, false, config); break;
         case DOT::TST_DOT: dot = new DotOpt(*temp, energyTerms, energyParams, false, config); opt = dot; break;
-        default: std::cerr << "driver supports timeStepper DOT and Newton only" << std::endl; return 1;
+        // the other L-BFGS initialisers that share the kernels (main.cpp:922-931)
+        case DOT::TST_LBFGSH: opt = new DOT::LBFGSTimeStepper<DIM>(*temp, energyTerms, energyParams, DOT::D0T_H, false, config); break;
+        case DOT::TST_LBFGSJH: {
+            auto* jh = new DOT::LBFGSTimeStepper<DIM>(*temp, energyTerms, energyParams, DOT::D0T_JH, false, config);
+            opt = jh;
+            if (!dumpDir.empty()) {  // node labels of METIS<3>::partMesh_nodes (LBFGSTimeStepper.cpp:71-74)
+                std::vector<long long> np(jh->nodePart.begin(), jh->nodePart.end());
+                mkdir(dumpDir.c_str(), 0777);
+                mkdir((dumpDir + "/setup").c_str(), 0777);
+                npy_i64(dumpDir + "/setup/npart.npy", {(long)np.size()}, np.data());
+            }
+            break;
+        }
+        default: std::cerr << "driver supports timeStepper DOT, Newton, LBFGSH and LBFGSJH only" << std::endl; return 1;
     }
     opt->setTime(config.duration, config.dt);
     opt->precompute();

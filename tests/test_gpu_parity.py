@@ -738,3 +738,40 @@ def test_set_fixed_reanalysis_matches_a_fresh_stepper():
         assert np.array_equal(xa, xb)
     assert np.abs(xa[right] - xs[right]).max() > 1e-6   # the released handle moves now
     assert np.array_equal(xa[fm2 > 0], xs[fm2 > 0])    # the other one stays where the script left it
+
+
+@pytest.mark.parametrize("name,method", [("small_snh_lbfgsh_twist", "LBFGSH"), ("small_fcr_lbfgsjh4_tsns", "LBFGSJH")])
+def test_lbfgs_initialisers_follow_reference(name, method):
+    """`timeStepper LBFGSH` / `LBFGSJH 4` (LBFGSTimeStepper.cpp:108-265, 339-420) on the device kernels - the global
+    projected Hessian / its block Jacobi over the METIS node partition as L-BFGS initialiser, steps starting at 1.  Node labels from
+    dotgpu_partition_nodes equal the reference's; from the reference's state after frame 1 the iteration log (17-digit iterStats) and
+    the positions are followed like DOT's."""
+    g = Golden(name)
+    V, T = g["setup/V_rest"], g["setup/F"]
+    a = D.Anim(g.meta["anim"], V)
+    npart = None
+    if method == "LBFGSJH":
+        npart = g["setup/npart"].astype(np.int32)
+        import os
+        if os.path.exists(os.path.join(os.path.dirname(D.lib_path()), "libdotmetis.so")):
+            assert np.array_equal(D.partition_nodes(V.shape[0], T, g.k), npart)
+    stp = D.Stepper(V, T, None, a.fixed_mask(), energy=g.meta["energy"], k=g.k, dt=g.meta["dt"], method=method, node_part=npart)
+    assert abs(stp.target - g.meta["stats"]["targetGRes"]) <= 1e-12 * stp.target
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    x = V.copy()
+    for _ in range(f0):
+        a.step(x, g.meta["dt"])
+    stp.set_state(g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    x = g["frame%d/V" % f0].copy()
+    ref_stats = g.iter_stats()
+    for f in range(f0 + 1, dumps[-1] + 1):
+        a.step(x, g.meta["dt"])
+        fs = stp.frame(x)
+        ref = ref_stats[ref_stats[:, 0] == f - 1]
+        log = stp.iter_log()
+        assert fs.converged == 1 and fs.iters == g.meta["stats"]["frame_iters"][f - 1], f
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-9, atol=0), f      # every step length (all 1 unless halved)
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-8), f
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3), f
+    assert np.abs(x - g["frame%d/V" % dumps[-1]]).max() < 1e-8

@@ -248,3 +248,29 @@ def test_time_stepping_follows_reference_through_line_search_halvings(name):
     assert stp.halvings > 0    # the comparison above went through the halving branch
     f = dumps[-1]
     assert np.abs(stp.x - g["frame%d/V" % f]).max() < tx
+
+
+LBFGS_CASES = [("small_snh_lbfgsh_twist", "H"), ("small_fcr_lbfgsjh4_tsns", "JH")]
+
+
+@pytest.mark.parametrize("name,d0", LBFGS_CASES)
+def test_lbfgs_initialisers_follow_reference_from_restart(name, d0):
+    """LBFGS-H / LBFGS-JH (LBFGSTimeStepper.cpp) - the oracle's restatement follows the reference's `timeStepper
+    LBFGSH` / `LBFGSJH 4` runs iteration by iteration from the state after frame 1 (17-digit iterStats): every step starts at 1."""
+    g = Golden(name)
+    m = mesh_of(g)
+    npart = g["setup/npart"] if d0 == "JH" else None
+    stp = O.LBFGSStepper(m, g.meta["energy"], d0, npart, g.meta["anim"], g.meta["dt"])
+    dumps = g.meta["dumps"]
+    f0 = dumps[0]
+    stp.restart(f0, g["frame%d/V" % f0], g["frame%d/velocity" % f0])
+    for f in range(f0 + 1, dumps[-1] + 1):
+        stp.log = []
+        it = stp.step_frame()
+        ref = _frame_rows(g, f)
+        log = np.asarray(stp.log)
+        assert it == g.meta["stats"]["frame_iters"][f - 1], f
+        assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-9, atol=0), f
+        assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-8), f
+        assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3 if d0 == "JH" else 1e-4), f
+    assert np.abs(stp.x - g["frame%d/V" % dumps[-1]]).max() < 1e-8
