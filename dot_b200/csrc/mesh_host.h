@@ -71,5 +71,7 @@ struct DDHost {
 void metis_partition(int nV, int nT, const int32_t* tets, int k, int32_t* epart_out);
 // METIS<3>::partMesh_nodes (METIS_PartMeshNodal with the same option vector, Utils/METIS.hpp:161-212): node labels [nV]
 void metis_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out);
+// multilevel vertex separator (METIS_ComputeVertexSeparator) for the fill-reducing ordering; false if libdotmetis.so is absent
+bool metis_vertex_separator(int n, const int64_t* xadj, const int64_t* adjncy, int64_t* part);
 
 }  // namespace dotgpu

@@ -30,6 +30,7 @@ constexpr int kMetisOK = 1;
 
 typedef int (*fn_defaults)(idx_t*);
 typedef int (*fn_partmeshdual)(idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, real_t*, idx_t*, idx_t*, idx_t*, idx_t*);
+typedef int (*fn_vsep)(idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*);
 typedef int (*fn_partmeshnodal)(idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, idx_t*, real_t*, idx_t*, idx_t*, idx_t*, idx_t*);
 
 struct MetisLib {
@@ -37,6 +38,8 @@ struct MetisLib {
     fn_defaults defaults = nullptr;
     fn_partmeshdual part = nullptr;
     fn_partmeshnodal part_nodal = nullptr;
+    fn_vsep vsep = nullptr;
+    std::mutex mtx;   // METIS 5.1.0 seeds a process-global RNG per call: calls are serialised so that every call is reproducible
     std::string err;
 };
 
@@ -62,6 +65,7 @@ MetisLib& metis() {
         L.defaults = (fn_defaults)dlsym(L.h, "METIS_SetDefaultOptions");
         L.part = (fn_partmeshdual)dlsym(L.h, "METIS_PartMeshDual");
         L.part_nodal = (fn_partmeshnodal)dlsym(L.h, "METIS_PartMeshNodal");
+        L.vsep = (fn_vsep)dlsym(L.h, "METIS_ComputeVertexSeparator");
         if (!L.defaults || !L.part) L.err = "libdotmetis.so lacks METIS_SetDefaultOptions / METIS_PartMeshDual";
     });
     return L;
@@ -69,10 +73,28 @@ MetisLib& metis() {
 
 }  // namespace
 
+// Multilevel vertex separator of a graph (METIS_ComputeVertexSeparator: MlevelNodeBisectionMultiple, the bisection step of METIS'
+// own nested dissection) for the fill-reducing ordering of chol_symbolic.cpp.  part[i] = 0 / 1 (the two sides) or 2 (separator).
+// Returns false when libdotmetis.so is not available (the caller falls back to its level-structure separators).
+bool metis_vertex_separator(int n, const int64_t* xadj, const int64_t* adjncy, int64_t* part) {
+    MetisLib& L = metis();
+    if (!L.h || !L.defaults || !L.vsep) return false;
+    std::lock_guard<std::mutex> lock(L.mtx);
+    idx_t options[kNOptions];
+    L.defaults(options);
+    options[OPT_SEED] = -1;
+    options[OPT_DBGLVL] = 0;
+    idx_t nv = n, sepsize = 0;
+    const int status = L.vsep(&nv, const_cast<idx_t*>((const idx_t*)xadj), const_cast<idx_t*>((const idx_t*)adjncy), nullptr, options, &sepsize,
+                              (idx_t*)part);
+    return status == kMetisOK;
+}
+
 static void metis_part(int nV, int nT, const int32_t* tets, int k, bool nodal, int32_t* out) {
     DG_REQUIRE(nV > 0 && nT > 0 && tets && out, "null or empty mesh");
     DG_REQUIRE(k >= 2, "the number of partitions must be at least 2 (METIS.hpp:300-302)");
     MetisLib& L = metis();
+    std::lock_guard<std::mutex> lock(L.mtx);
     if (!L.h || !L.defaults || !L.part || !L.part_nodal)
         throw Error(DOTGPU_ERR_STATE, "libdotmetis.so (the reference's vendored METIS 5.1.0, built by dot_b200/build.py) is not available: " + L.err +
                                           "; pass labels produced elsewhere instead");
