@@ -96,6 +96,8 @@ def main(argv=None):
             stp.set_rel_tol(cur_tol)
         xt_prev = stp.get_state()[2]          # xTilta of this time step (dx_Elastic = x - xTilta, Optimizer.cpp:356)
         anim.step(x, s.dt)
+        if anim.changed:                      # the script changed the Dirichlet set: updatePrecondMtrAndFactorize (Optimizer.cpp:334-336)
+            stp.set_fixed(anim.fixed_mask(), x)
         fs = stp.frame(x)
         dxe = x - xt_prev
         iters += fs.iters

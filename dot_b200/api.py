@@ -11,7 +11,7 @@ _LIB = None
 
 ENERGY_FCR, ENERGY_SNH = 0, 1
 ANIM_KINDS = {"null": 0, "stretch": 1, "squash": 2, "stretchnsquash": 3, "twist": 4, "twistnstretch": 5, "twistnsns": 6,
-              "twistnsns_old": 7}
+              "twistnsns_old": 7, "rubberBandPull": 8}
 _ENERGY = {"FCR": ENERGY_FCR, "SNH": ENERGY_SNH, 0: 0, 1: 1}
 
 
@@ -317,7 +317,9 @@ class Anim:
     def step(self, x, dt):
         """stepAnimScript: moves the handle rows of x in place (x: [nV,3] float64 C-contiguous)."""
         assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]
-        _chk(lib().dotgpu_anim_step(self.h, _p(x), C.c_double(dt)))
+        flag = C.c_int(0)
+        _chk(lib().dotgpu_anim_step_ex(self.h, _p(x), C.c_double(dt), C.byref(flag)))
+        self.changed = bool(flag.value)     # the Dirichlet set changed in this step (rubberBandPull): call Stepper.set_fixed(anim.fixed_mask(), x)
         return x
 
 

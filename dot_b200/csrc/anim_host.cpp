@@ -10,7 +10,7 @@ namespace dotgpu {
 void AnimHost::init(int kind_, int nV_, const double* V, double ratio) {
     kind = kind_;
     nV = nV_;
-    if (kind < DOTGPU_ANIM_NULL || kind > DOTGPU_ANIM_TWISTNSNS_OLD) throw std::invalid_argument("unknown anim script");
+    if (kind < DOTGPU_ANIM_NULL || kind > DOTGPU_ANIM_RUBBERBANDPULL) throw std::invalid_argument("unknown anim script");
     double lo[3], hi[3];
     for (int c = 0; c < 3; ++c) lo[c] = hi[c] = V[c];
     for (int v = 1; v < nV; ++v)
@@ -20,6 +20,33 @@ void AnimHost::init(int kind_, int nV_, const double* V, double ratio) {
         }
     for (int c = 0; c < 3; ++c) center[c] = (lo[c] + hi[c]) / 2.0;  // bbox.colwise().mean()
     handles.assign(2, {});
+    fixed_now.assign(nV, 0);
+    if (kind == DOTGPU_ANIM_RUBBERBANDPULL) {
+        // AnimScripter.cpp:219-257: bottom and top 2 % of the y range are pulled apart at -/+ 0.2 (handleVerts[1]), the waist
+        // (0.48..0.52 of the y range) is dragged in -x at 2.5 (handleVerts[0]) until its first vertex has moved by 5, then released
+        const double ry = hi[1] - lo[1];
+        bool turning_set = false;
+        for (int v = 0; v < nV; ++v) {
+            const double y = V[3 * (size_t)v + 1];
+            if (y < lo[1] + ry * 0.02) {
+                handles[1].push_back(v); velx[v] = 0.0; vely[v] = -0.2;
+            } else if (y > hi[1] - ry * 0.02) {
+                handles[1].push_back(v); velx[v] = 0.0; vely[v] = 0.2;
+            } else if (y < hi[1] - ry * 0.48 && y > lo[1] + ry * 0.48) {
+                handles[0].push_back(v); velx[v] = -2.5; vely[v] = 0.0;
+                if (!turning_set) {
+                    turning_set = true;
+                    has_turn = true;
+                    turn_v = v;
+                    turn_lo = V[3 * (size_t)v] - 5.0;
+                }
+            }
+        }
+        if (!turning_set) throw std::invalid_argument("rubberBandPull: no vertex in the waist band");
+        for (auto& h : handles)
+            for (int v : h) fixed_now[v] = 1;
+        return;
+    }
     const double range = hi[0] - lo[0];
     for (int v = 0; v < nV; ++v) {
         double xv = V[3 * (size_t)v];
@@ -52,20 +79,29 @@ void AnimHost::init(int kind_, int nV_, const double* V, double ratio) {
         turn_lo = V[3 * (size_t)turn_v] - (kind == DOTGPU_ANIM_TWISTNSNS ? 1.2 : 0.8);
         turn_hi = V[3 * (size_t)turn_v] + 0.4;
     }
+    if (kind == DOTGPU_ANIM_NULL) fixed_now[0] = 1;  // Mesh::computeFeatures default (Mesh.cpp:593-599)
+    for (auto& h : handles)
+        for (int v : h) fixed_now[v] = 1;
 }
 
 void AnimHost::fixed_mask(uint8_t* out) const {
-    for (int v = 0; v < nV; ++v) out[v] = 0;
-    if (kind == DOTGPU_ANIM_NULL) {
-        out[0] = 1;  // Mesh::computeFeatures default (Mesh.cpp:593-599)
-        return;
-    }
-    for (auto& h : handles)
-        for (int v : h) out[v] = 1;
+    for (int v = 0; v < nV; ++v) out[v] = fixed_now[v];
 }
 
-void AnimHost::step(double* x, double dt) {
+int AnimHost::step(double* x, double dt) {
     std::vector<double> d(3 * (size_t)nV, 0.0);
+    if (kind == DOTGPU_ANIM_RUBBERBANDPULL) {  // AnimScripter.cpp:404-423
+        int flag = 0;
+        if (!released && x[3 * (size_t)turn_v] <= turn_lo) {
+            released = true;
+            for (int v : handles[0]) { fixed_now[v] = 0; velx[v] = 0.0; vely[v] = 0.0; }
+            for (int v : handles[1]) { velx[v] = 0.0; vely[v] = 0.0; }
+            flag = 1;
+        }
+        for (auto& kv : velx) x[3 * (size_t)kv.first] += 1.0 * (kv.second * dt);
+        for (auto& kv : vely) x[3 * (size_t)kv.first + 1] += 1.0 * (kv.second * dt);
+        return flag;
+    }
     for (auto& kv : ang) {
         // Eigen::AngleAxis(angle, UnitX).toRotationMatrix(), term by term
         const double angle = kv.second * dt, c = std::cos(angle), s = std::sin(angle), c1 = 1.0 - c;
@@ -87,6 +123,7 @@ void AnimHost::step(double* x, double dt) {
         d[3 * (size_t)kv.first] += kv.second * dt;
     }
     for (size_t i = 0; i < d.size(); ++i) x[i] += 1.0 * d[i];
+    return 0;
 }
 
 }  // namespace dotgpu

@@ -443,6 +443,13 @@ int dotgpu_anim_step(dotgpu_anim* a, double* x_inout, double dt) {
     a->a.step(x_inout, dt);
     API_END
 }
+int dotgpu_anim_step_ex(dotgpu_anim* a, double* x_inout, double dt, int* dirichlet_set_changed) {
+    API_BEGIN
+    DG_REQUIRE(a && x_inout, "null argument");
+    const int f = a->a.step(x_inout, dt);
+    if (dirichlet_set_changed) *dirichlet_set_changed = f;
+    API_END
+}
 
 // ---------------------------------------------------------------- stepper
 void dotgpu_stepper_default_config(dotgpu_stepper_config* c) {

@@ -23,7 +23,7 @@ import numpy as np
 ENERGIES = {"FCR": "FCR", "SNH": "SNH"}
 # `script` names -> AnimScripter kinds known to libdotgpu (AnimScripter.cpp:29-76)
 ANIM_SCRIPTS = {"null": "null", "stretch": "stretch", "squash": "squash", "stretchnsquash": "stretchnsquash", "twist": "twist",
-                "twistnstretch": "twistnstretch", "twistnsns": "twistnsns", "twistnsns_old": "twistnsns_old"}
+                "twistnstretch": "twistnstretch", "twistnsns": "twistnsns", "twistnsns_old": "twistnsns_old", "rubberBandPull": "rubberBandPull"}
 
 
 @dataclass

@@ -44,6 +44,7 @@ extern "C" {
 #define DOTGPU_ANIM_TWISTNSTRETCH 5
 #define DOTGPU_ANIM_TWISTNSNS 6
 #define DOTGPU_ANIM_TWISTNSNS_OLD 7
+#define DOTGPU_ANIM_RUBBERBANDPULL 8 /* changes the Dirichlet set mid-run (AnimScripter.cpp:219-257, 404-423) */
 
 const char* dotgpu_last_error(void);
 int dotgpu_version(void);
@@ -155,6 +156,9 @@ int dotgpu_anim_create(dotgpu_anim** out, int kind, int nV, const double* V_rest
 void dotgpu_anim_destroy(dotgpu_anim* a);
 int dotgpu_anim_fixed_mask(dotgpu_anim* a, uint8_t* mask_out);    /* [nV] */
 int dotgpu_anim_step(dotgpu_anim* a, double* x_inout, double dt); /* stepAnimScript: moves handle rows of x */
+/* same, and *dirichlet_set_changed = AnimScripter::stepAnimScript's return value: 1 when the script released / added handles in this step
+ * (rubberBandPull).  The caller then fetches the new set with dotgpu_anim_fixed_mask and calls dotgpu_stepper_set_fixed (Optimizer.cpp:334-336). */
+int dotgpu_anim_step_ex(dotgpu_anim* a, double* x_inout, double dt, int* dirichlet_set_changed);
 
 /* ------------------------------------------------------------------------------------------
  * Device-resident DOT time stepper: sits under Optimizer<3>'s virtuals precompute / fullyImplicit /

@@ -646,6 +646,25 @@ class AnimScripter:
         sgn = [1.0, -1.0]
         self.ang = {}
         self.vel = {}
+        self.changed = False
+        self.released = False
+        if kind == "rubberBandPull":                                     # AnimScripter.cpp:219-257
+            lo, hi = V.min(axis=0), V.max(axis=0)
+            ry = hi[1] - lo[1]
+            waist, ends = [], []
+            for v in range(V.shape[0]):
+                y = V[v, 1]
+                if y < lo[1] + ry * 0.02:
+                    ends.append(v); self.vel[v] = np.array([0.0, -0.2, 0.0])
+                elif y > hi[1] - ry * 0.02:
+                    ends.append(v); self.vel[v] = np.array([0.0, 0.2, 0.0])
+                elif hi[1] - ry * 0.48 > y > lo[1] + ry * 0.48:
+                    waist.append(v); self.vel[v] = np.array([-2.5, 0.0, 0.0])
+            self.handles = [np.array(waist, dtype=np.int32), np.array(ends, dtype=np.int32)]
+            self.ang = {}
+            self.turn = (int(waist[0]), V[waist[0], 0] - 5.0, np.inf)
+            self.fixed_now = np.sort(np.concatenate(self.handles)).astype(np.int32)
+            return
         spec = {"twist": (-0.1 * math.pi, None), "stretch": (None, -0.1), "squash": (None, 0.03),
                 "twistnstretch": (-0.1 * math.pi, -0.1), "twistnsns": (-0.4 * math.pi, -1.2),
                 "twistnsns_old": (-0.4 * math.pi, -0.9), "stretchnsquash": (None, -0.9), "null": (None, None)}[kind]
@@ -664,10 +683,24 @@ class AnimScripter:
     def fixed(self):
         if self.kind == "null":
             return np.array([0], dtype=np.int32)
+        if self.kind == "rubberBandPull":
+            return self.fixed_now
         return np.sort(np.concatenate(self.handles)).astype(np.int32)
 
     def step(self, x, dt):
         d = np.zeros_like(x)
+        self.changed = False
+        if self.kind == "rubberBandPull":                                # AnimScripter.cpp:404-423
+            v0, lo, _ = self.turn
+            if not self.released and x[v0, 0] <= lo:
+                self.released = True
+                self.changed = True
+                for v in self.vel:
+                    self.vel[v] = np.zeros(3)
+                self.fixed_now = np.sort(self.handles[1]).astype(np.int32)
+            for v in self.vel:
+                d[v] += self.vel[v] * dt
+            return x + 1.0 * d
         for v, w in self.ang.items():
             R = rot_x(w * dt)
             d[v] = (R @ (x[v] - self.center) + self.center) - x[v]

@@ -47,6 +47,9 @@ HALVING_CASES = [
     ("small_snh_k4_twist_dt200", "bar_small", "SNH", 4, "twist", 6, [1, 6], 16, 0.2),
     ("small_fcr_k3_tsns_dt200", "bar_small", "FCR", 3, "twistnsns", 8, [1, 8], 16, 0.2),
 ]
+# a15 / DOTTimeStepper::updatePrecondMtrAndFactorize: `script rubberBandPull` drags the waist of the bar 5 units sideways and RELEASES it
+# at time step 81 (the Dirichlet set changes mid-run -> new patterns, symbolic analysis, factorisation); default tol, 17-digit iterStats
+RUBBER_CASES = [("bar2K_snh_k4_rubberband", "bar2K", "SNH", 4, "rubberBandPull", 83, [79, 80, 81, 83], 4, 0.025)]
 # the reference's own input meshes (BASELINE.json configs C1, C2, C5): nodes / tets as parsed from input/tetMeshes/*.msh
 # plus the METIS labels of the reference's wrapper for the subdomain counts the configs name
 MESH_CASES = [("bunny5K", [6]), ("bar17K", [8]), ("horse38K", [16])]
@@ -93,7 +96,7 @@ def make_mesh(tmp, preset):
     return V, T, msh
 
 
-def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepper="DOT", full_precision=False):
+def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepper="DOT", full_precision=False, tol=None):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
         V, T, msh = make_mesh(tmp, preset)
@@ -106,6 +109,8 @@ def gen_case(name, preset, energy, parts, anim, frames, dumps, he_cap, dt, stepp
             args += ["--stepper", stepper]
         if full_precision:
             args += ["--full-precision"]
+        if tol is not None:
+            args += ["--tol", repr(tol)]
         stats = run_ref(args, tmp)
         arrs = collect(dd)
         arrs["iterStats"] = np.array(open(os.path.join(dd, "iterStats.txt")).read())
@@ -230,6 +235,15 @@ if __name__ == "__main__":
     for c in HALVING_CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c, full_precision=True)
+    for c in RUBBER_CASES:
+        if not a.only or a.only in c[0]:
+            gen_case(*c, full_precision=True)
+            # keep the states only (positions, velocities, Dirichlet sets): the matrices of 4 dumped frames would be 7 MB
+            pth = os.path.join(GOLD, c[0] + ".npz")
+            z = np.load(pth)
+            keep = {k: z[k] for k in z.files if k in ("meta", "iterStats", "setup/V_rest", "setup/F", "setup/epart") or
+                    (k.startswith("frame") and k.split("/")[1] in ("V", "velocity", "fixed", "xTilta"))}
+            np.savez_compressed(pth, **keep)
     for c in LBFGS_CASES:
         if not a.only or a.only in c[0]:
             gen_case(*c[:9], stepper=c[9], full_precision=True)

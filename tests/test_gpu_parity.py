@@ -775,3 +775,56 @@ def test_lbfgs_initialisers_follow_reference(name, method):
         assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-8), f
         assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3), f
     assert np.abs(x - g["frame%d/V" % dumps[-1]]).max() < 1e-8
+
+
+def test_rubber_band_release_changes_the_dirichlet_set_mid_run():
+    """a15 + DOTTimeStepper::updatePrecondMtrAndFactorize on the device: `script rubberBandPull` on a 5,184-tet bar.  From the
+    reference's state after time step 80 the device stepper takes step 81 - the step in which the script RELEASES the waist handle
+    (AnimScripter returns 1 -> dotgpu_stepper_set_fixed: new patterns, symbolic analysis, Hessians and factorisation at result.V,
+    Optimizer.cpp:334-336) - and steps 82, 83.  The release step is a violent snap-back (2,870 reference iterations, ~1,000 halvings):
+    iteration paths are not comparable there, both runs converge to the reference's stopping criterion; the converged positions
+    agree to the solver tolerance and the step before the release is followed iteration by iteration."""
+    g = Golden("bar2K_snh_k4_rubberband")
+    V, T, ep = g["setup/V_rest"], g["setup/F"], g["setup/epart"]
+    dt = g.meta["dt"]
+    a = D.Anim("rubberBandPull", V)
+    stp = D.Stepper(V, T, ep, a.fixed_mask(), energy="SNH", k=g.k, dt=dt)
+    x = V.copy()
+    for f in range(1, 80):                       # replay the script up to the reference's dumped state
+        a.step(x, dt)
+        assert not a.changed
+    stp.set_state(g["frame79/V"], g["frame79/velocity"])
+    x = g["frame79/V"].copy()
+    ref_stats = g.iter_stats()
+    # step 80: still pulling - exact path
+    a.step(x, dt)
+    assert not a.changed
+    fs = stp.frame(x)
+    ref = ref_stats[ref_stats[:, 0] == 79]
+    log = stp.iter_log()
+    assert fs.converged == 1 and fs.iters == g.meta["stats"]["frame_iters"][79]
+    assert np.allclose(log[:, 0], ref[:, 1], rtol=1e-6, atol=0) and np.allclose(log[:, 1], ref[:, 2], rtol=1e-9)
+    assert np.abs(x - g["frame80/V"]).max() < 1e-8
+    # step 81: the release
+    stp.set_state(g["frame80/V"], g["frame80/velocity"])
+    x = g["frame80/V"].copy()
+    a.step(x, dt)
+    assert a.changed
+    fm = a.fixed_mask()
+    assert np.array_equal(np.nonzero(fm)[0], np.sort(g["frame81/fixed"]))
+    stp.set_fixed(fm, x)
+    fs = stp.frame(x)
+    it_ref = g.meta["stats"]["frame_iters"][80]
+    assert fs.converged == 1 and fs.halvings > 0
+    assert 0.5 * it_ref <= fs.iters <= 2.0 * it_ref, (fs.iters, it_ref)
+    err81 = float(np.abs(x - g["frame81/V"]).max())
+    assert np.array_equal(x[fm > 0], g["frame81/V"][fm > 0])
+    for f in (82, 83):
+        a.step(x, dt)
+        assert not a.changed
+        assert stp.frame(x).converged == 1
+    err83 = float(np.abs(x - g["frame83/V"]).max())
+    # converged-state agreement at the default tolerance 1e-5 (SURVEY 8(c): the reference itself moves by ~1e-3 under such changes).
+    # Measured on B200: 5.9e-3 right after the snap-back (the waist had been dragged 5 units: 1e-3 of the displacement), 1.6e-4 two
+    # steps later when the band has settled.
+    assert err81 < 2e-2 and err83 < 1e-3, (err81, err83)

@@ -274,3 +274,35 @@ def test_lbfgs_initialisers_follow_reference_from_restart(name, d0):
         assert np.allclose(log[:, 1], ref[:, 2], rtol=1e-8), f
         assert np.allclose(log[:, 2], ref[:, 3], rtol=1e-3 if d0 == "JH" else 1e-4), f
     assert np.abs(stp.x - g["frame%d/V" % dumps[-1]]).max() < 1e-8
+
+
+def test_rubber_band_pull_script_releases_the_waist_like_the_reference():
+    """a15: `script rubberBandPull` (AnimScripter.cpp:219-257, 404-423) - the only shipped script that CHANGES the Dirichlet set
+    mid-run.  Host AnimScripter of libdotgpu and the oracle's restatement against the reference's dumped Dirichlet sets and handle
+    positions: before the release (time steps 79, 80), at the release (81: the waist handle is freed, every handle stops) and after."""
+    import dot_b200 as D
+    g = Golden("bar2K_snh_k4_rubberband")
+    V = g["setup/V_rest"]
+    a = D.Anim("rubberBandPull", V)
+    o = O.AnimScripter("rubberBandPull", V, None)
+    assert np.array_equal(np.nonzero(a.fixed_mask())[0], o.fixed())
+    x, xo = V.copy(), V.copy()
+    changed_at = []
+    for f in range(1, 84):
+        a.step(x, g.meta["dt"])
+        xo = o.step(xo, g.meta["dt"])
+        if a.changed:
+            changed_at.append(f)
+        assert a.changed == o.changed
+        fixed = np.nonzero(a.fixed_mask())[0]
+        assert np.array_equal(fixed, o.fixed())
+        if g.has("frame%d/fixed" % f):
+            ref_fixed = np.sort(g["frame%d/fixed" % f])
+            assert np.array_equal(fixed, ref_fixed), f
+            # Dirichlet rows are exactly where the script put them (the solve never moves them)
+            assert np.abs(x[fixed] - g["frame%d/V" % f][fixed]).max() < 1e-12, f
+            assert np.abs(xo[fixed] - g["frame%d/V" % f][fixed]).max() < 1e-12, f
+        # free vertices follow the reference where it was dumped so that the handle test above stays meaningful
+        if g.has("frame%d/V" % f):
+            x, xo = g["frame%d/V" % f].copy(), g["frame%d/V" % f].copy()
+    assert changed_at == [81]
