@@ -103,7 +103,8 @@ struct CholBatch {
     // x_perm: device vector of n_total doubles in the PERMUTED order of each matrix (x_perm[col_off[m] + i] = x_m[perm_m[i]]).
     // Right-hand side: entry i of the permuted concatenation is b[gidx[i]] (gather fused into the solve), or b[i] when
     // gidx == nullptr (then b is already permuted and b == x_perm is allowed).
-    void solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st);
+    // go: optional device flag; *go == 0 turns the whole solve into a no-op (speculatively enqueued L-BFGS iterations, linalg.h)
+    void solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st, const int* go = nullptr);
     // level-by-level reference implementation of the same solve (one launch per level and direction); kept as the
     // in-library cross-check of the streamed kernel
     void solve_levels(const double* b_perm, double* x_perm, cudaStream_t st);

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
     k_solve_stream(int ngroups, const SolveTask* __restrict__ chunks, const int* __restrict__ rows,
                    const int* __restrict__ rel, const double* __restrict__ Pf, const double* __restrict__ Pb, const double* __restrict__ b,
                    const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, unsigned* claim, int stage_dbl,
-                   int vec_dbl, int dbg) {
+                   int vec_dbl, int dbg, const int* __restrict__ go) {
+    if (go && *go == 0) return;  // speculatively enqueued iteration whose assumption failed (linalg.h): every CTA leaves at once
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);          // NSTAGE * stage_dbl
     double* vecs = ring + (size_t)NSTAGE * stage_dbl;             // 2 x [vec_dbl] vectors (double-buffered across supernodes)
@@ -368,7 +369,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
 // right-hand side in the permuted, concatenated numbering of the factors: b_perm[i] = b[gidx[i]] - the gatherers then read
 // contiguous ranges (one latency on the critical path of every supernode instead of two dependent ones)
 __global__ void __launch_bounds__(256) k_gather_rhs(long long n, const double* __restrict__ b, const int* __restrict__ gidx,
-                                                    double* __restrict__ out) {
+                                                    double* __restrict__ out, const int* __restrict__ go) {
+    if (go && *go == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = b[gidx[i]];
 }
@@ -456,7 +458,7 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
     // configurations bigger stages win (bar1M: 0.78 ms at 24 KB vs 0.85 ms at 20 KB).
     const int vec_bytes = 24 * (((max_front_all + 8 + 15) / 16) * 16);
     int auto_stage = ((73 * 1024 - vec_bytes) / 16) / 256 * 256;
-    auto_stage = std::max(1536, std::min(3072, auto_stage));
+    auto_stage = std::max(1536, std::min(3584, auto_stage));  // r2 sweep on bar1M: 3072 -> 0.714 ms, 3584 -> 0.676 ms, 3840 (2 CTAs/SM) -> 0.890 ms
     const int want_stage = env_int("DOTGPU_SOLVE_STAGE_DBL", auto_stage);
     solve_dbg = env_int("DOTGPU_SOLVE_DBG", 0);  // experiments only: 1 skip the products, 2 skip the TMA copies, 4 skip dependency waits
     solve_nstage = std::min(4, std::max(2, env_int("DOTGPU_SOLVE_NSTAGE", 2)));
@@ -617,12 +619,12 @@ void CholBatch::pack_panels(int level, cudaStream_t st) {
     count_launch();
 }
 
-void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st) {
+void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStream_t st, const int* go) {
     if (!factorized) throw Error(DOTGPU_ERR_STATE, "solve before factorize");
     if (!n_solve_tasks) return;
     static const bool pre_gather = std::getenv("DOTGPU_SOLVE_NO_PREGATHER") == nullptr;
     if (gidx && pre_gather) {
-        k_gather_rhs<<<ceil_div(n_total, 256), 256, 0, st>>>(n_total, b, gidx, rwork.p);
+        k_gather_rhs<<<ceil_div(n_total, 256), 256, 0, st>>>(n_total, b, gidx, rwork.p, go);
         count_launch();
         b = rwork.p;
         gidx = nullptr;
@@ -631,7 +633,7 @@ void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStre
     unsigned* claim = d_cnt.p + 3 * (size_t)std::max(nsuper_total, 1);
 #define DG_SOLVE_LAUNCH(NS)                                                                                                         \
     k_solve_stream<NS><<<solve_grid, SOLVE_THREADS, solve_smem, st>>>(n_solve_tasks, d_stasks.p, d_rows.p, d_rel.p, Pf.p, Pb.p, b, \
-                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg)
+                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg, go)
     if (solve_nstage == 2) DG_SOLVE_LAUNCH(2);
     else if (solve_nstage == 3) DG_SOLVE_LAUNCH(3);
     else DG_SOLVE_LAUNCH(4);

@@ -45,7 +45,8 @@ void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, doubl
 struct HistList;
 void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
-                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st);
+                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st,
+                          int* flag_out = nullptr, double target = 0.0);
 void launch_svd(DeviceMesh& m, const double* x, double* F, double* U, double* S, double* V, cudaStream_t st);
 // fills m.He ([nT][10][9])
 void launch_elem_hessians(DeviceMesh& m, const double* x, double coef, bool project, cudaStream_t st);

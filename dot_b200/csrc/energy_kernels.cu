@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(TPB) k_grad_block(int nT, const int4* __restri
                                                     const double* __restrict__ lam, const double* __restrict__ x, double coef,
                                                     const int* __restrict__ lv_ptr, const unsigned short* __restrict__ cptr,
                                                     const unsigned short* __restrict__ cidx, double* __restrict__ part,
-                                                    double* __restrict__ epartial) {
+                                                    double* __restrict__ epartial, const int* __restrict__ go) {
+    if (go && *go == 0) return;  // speculatively enqueued iteration whose assumption failed (linalg.h)
     __shared__ double sg[12 * TPB];
     __shared__ double she[TPB / 32];
     const int t = blockIdx.x * TPB + threadIdx.x;
@@ -218,7 +219,12 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
                                                           double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                           const double* __restrict__ alpha_dev, double alpha_host, HistList H,
                                                           double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
-                                                          const double* __restrict__ epartial, int n_epartial, double coef) {
+                                                          const double* __restrict__ epartial, int n_epartial, double coef,
+                                                          int* __restrict__ flag_out, double target) {
+    if (H.go && *H.go == 0) {  // the speculation behind this iteration failed: pass the "stop" on to whatever was enqueued behind it
+        if (flag_out && blockIdx.x == 0 && threadIdx.x == 0) *flag_out = 0;
+        return;
+    }
     constexpr int NACC = 4 + 3 * LB_MAXH;  // gg, ys, s.g, inertia energy, then per history pair: s_i.y, s.y_i, s_i.g
     __shared__ double shm[8 * NACC], res[NACC];
     __shared__ bool last;
@@ -271,7 +277,17 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
         for (int i = threadIdx.x; i < n_epartial; i += 32) v += __ldcg(epartial + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) sc[SC_E] = coef * v + res[3];
+        if (threadIdx.x == 0) {
+            const double Enew = coef * v + res[3];
+            sc[SC_E] = Enew;
+            if (flag_out) {
+                // what the host will decide when it sees these numbers (stepper.cu): step accepted without halving, pair kept,
+                // not converged -> the iteration enqueued behind this one may run
+                const int ok = (Enew <= sc[SC_EPREV]) && (sl < 0 || res[1] > 0.0) && (res[0] > target);
+                if (ok) sc[SC_EPREV] = Enew;
+                *flag_out = ok;
+            }
+        }
     }
     if ((int)threadIdx.x < nacc) {
         const int j = threadIdx.x;
@@ -489,21 +505,22 @@ void launch_energy_per_elem(DeviceMesh& m, const double* x, double* out, cudaStr
 void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, cudaStream_t st) {
     int nb = ceil_div(m.nT, TPB);
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
-                m.g_cptr.p, m.g_cidx.p, m.gpart.p, (double*)nullptr);
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p, (double*)nullptr, (const int*)nullptr);
     k_grad_vertex<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g);
     count_launch();
 }
 
 void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
-                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st) {
+                          const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st,
+                          int* flag_out, double target) {
     int nb = ceil_div(m.nT, TPB);
     if (with_energy && m.epart.n < (size_t)nb) m.epart.alloc(nb);
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
-                m.g_cptr.p, m.g_cidx.p, m.gpart.p, with_energy ? m.epart.p : (double*)nullptr);
+                m.g_cptr.p, m.g_cidx.p, m.gpart.p, with_energy ? m.epart.p : (double*)nullptr, H.go);
     k_grad_vertex_pair<<<multidot_blocks(m.nV), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g, pdir,
                                                               g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc,
-                                                              with_energy ? m.epart.p : (const double*)nullptr, nb, coef);
+                                                              with_energy ? m.epart.p : (const double*)nullptr, nb, coef, flag_out, target);
     count_launch();
 }
 

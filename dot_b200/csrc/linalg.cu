@@ -204,6 +204,7 @@ constexpr int MD_MAX_BLOCKS = 296;  // 2 CTAs per SM
 
 __global__ void __launch_bounds__(MD_TPB) k_dots(long long n, DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
                                                  double* __restrict__ sc) {
+    if (P.go && *P.go == 0) return;
     __shared__ double sh[8 * 12], res[12];
     __shared__ bool last;
     double acc[12];
@@ -230,6 +231,7 @@ __device__ __forceinline__ void lbfgs_xi(const double* __restrict__ sc, const Hi
 
 __global__ void __launch_bounds__(256) k_lbfgs_q(long long n, double* __restrict__ q, const double* __restrict__ g, HistList H,
                                                  double* __restrict__ sc) {
+    if (H.go && *H.go == 0) return;
     __shared__ double xi[LB_MAXH];
     if (threadIdx.x == 0) {
         lbfgs_xi(sc, H, xi);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(256) k_lbfgs_q(long long n, double* __restrict
 }
 
 __global__ void __launch_bounds__(256) k_lbfgs_p(long long n, double* __restrict__ p, HistList H, double* __restrict__ sc) {
+    if (H.go && *H.go == 0) return;
     __shared__ double c[LB_MAXH];
     if (threadIdx.x == 0) {
         // compact second loop: beta_i = (y_i . p_i) / (y_i . s_i),  y_i . p_i = y_i . p0 + sum_{j older than i} c_j (y_i . s_j),  c_i = xi_i - beta_i
@@ -268,7 +271,9 @@ __global__ void __launch_bounds__(256) k_lbfgs_p(long long n, double* __restrict
 
 __global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __restrict__ ia, const int* __restrict__ ja,
                                                         const double* __restrict__ a, const double* __restrict__ p,
-                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
+                                                        const int* __restrict__ go) {
+    if (go && *go == 0) return;
     __shared__ double sh[8];
     __shared__ bool last;
     int i = blockIdx.x * 256 + threadIdx.x;
@@ -301,7 +306,8 @@ __global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __rest
 }
 
 __global__ void k_axpy_dev(long long n, double* __restrict__ out, const double* __restrict__ x0, const double* __restrict__ p,
-                           const double* __restrict__ alpha_dev, double alpha_host) {
+                           const double* __restrict__ alpha_dev, double alpha_host, const int* __restrict__ go) {
+    if (go && *go == 0) return;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
     if (i < n) out[i] = x0[i] + alpha * p[i];
@@ -311,6 +317,7 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
                                                       const double* __restrict__ go, double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                       const double* __restrict__ alpha_dev, double alpha_host, HistList H,
                                                       double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    if (H.go && *H.go == 0) return;
     __shared__ double shm[8 * (2 + 2 * LB_MAXH)], res[2 + 2 * LB_MAXH];
     __shared__ bool last;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
@@ -354,6 +361,7 @@ __global__ void __launch_bounds__(MD_TPB) k_scatter_dots(int ndof, const int* __
                                                          const double* __restrict__ xs, const int* __restrict__ dup, double* __restrict__ p,
                                                          DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
                                                          double* __restrict__ sc) {
+    if (P.go && *P.go == 0) return;
     __shared__ double shm[8 * 12], res[12];
     __shared__ bool last;
     double acc[12];
@@ -410,13 +418,13 @@ void launch_lbfgs_q(long long n, double* q, const double* g, const HistList& H, 
 }
 void launch_lbfgs_p(long long n, double* p, const HistList& H, double* sc, cudaStream_t st) { EW_LAUNCH(k_lbfgs_p, n, n, p, H, sc); }
 void launch_quadform_alpha(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, unsigned* counter,
-                           double* sc, cudaStream_t st) {
-    k_quadform_alpha<<<ceil_div(n, 256), 256, 0, st>>>(n, ia, ja, a, p, partial, counter, sc);
+                           double* sc, cudaStream_t st, const int* go) {
+    k_quadform_alpha<<<ceil_div(n, 256), 256, 0, st>>>(n, ia, ja, a, p, partial, counter, sc, go);
     count_launch();
 }
 void launch_axpy_dev(long long n, double* out, const double* x0, const double* p, const double* alpha_dev, double alpha_host,
-                     cudaStream_t st) {
-    EW_LAUNCH(k_axpy_dev, n, n, out, x0, p, alpha_dev, alpha_host);
+                     cudaStream_t st, const int* go) {
+    EW_LAUNCH(k_axpy_dev, n, n, out, x0, p, alpha_dev, alpha_host, go);
 }
 void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
                       const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,

@@ -40,13 +40,18 @@ void launch_velocity(int nV, double* vel, const double* x, const double* xn, dou
 // ---- fused L-BFGS iteration kernels (compact two-loop recursion: all inner products of an iteration are taken in two
 // multi-dot passes against the Gram matrix of the history, DOTTimeStepper.cpp:389-398, 459-466 restated) ----
 constexpr int LB_MAXH = 8;
+// Speculative enqueue (stepper.cu): the kernels of iteration i+1 are launched before the host has seen the result of iteration i.
+// They carry a pointer `go` to a device flag written by the LAST kernel of iteration i (1: the step was accepted, the new pair kept,
+// not converged - exactly what the host assumed when it enqueued them); with *go == 0 every kernel returns at once.  go == nullptr: run.
 struct HistList {            // active pairs, oldest -> newest, as buffer slots
+    const int* go;
     int n;
     int slot[LB_MAXH];
     const double* S[LB_MAXH];  // by position
     const double* Y[LB_MAXH];
 };
 struct DotPairs {
+    const int* go;
     int n;
     const double* a[12];
     const double* b[12];
@@ -59,7 +64,8 @@ enum ScalarSlot {
     SC_YP = 16,   // y_i . p0     by slot
     SC_XI = 24,   // first-loop coefficients by slot
     SC_SY = 32,   // Gram matrix (s_i . y_j) at [SC_SY + 8*i + j], by slots
-    SC_COUNT = 96
+    SC_COUNT = 96,
+    SC_EPREV = 7   // energy of the last accepted point (speculative iterations compare against it on the device); shares the slot of SC_DOT
 };
 int multidot_partial_count();
 int multidot_blocks(long long n);  // fixed grid of the deterministic multi-reduction kernels
@@ -71,10 +77,10 @@ void launch_lbfgs_q(long long n, double* q, const double* g, const HistList& H, 
 void launch_lbfgs_p(long long n, double* p, const HistList& H, double* sc, cudaStream_t st);
 // sc[SC_PHP] = p^T A p and sc[SC_ALPHA] = clamp(-sc[SC_PG] / sc[SC_PHP], 0.1, 1)   (Optimizer::initStepSize, Optimizer.cpp:1076-1093)
 void launch_quadform_alpha(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, unsigned* counter,
-                           double* sc, cudaStream_t st);
+                           double* sc, cudaStream_t st, const int* go = nullptr);
 // out = x0 + alpha p with alpha read from the device (alpha_dev) or given (alpha_dev == nullptr)
 void launch_axpy_dev(long long n, double* out, const double* x0, const double* p, const double* alpha_dev, double alpha_host,
-                     cudaStream_t st);
+                     cudaStream_t st, const int* go = nullptr);
 // new pair s = alpha p, y = g_new - g_old written to S_new / Y_new, and in the same pass: sc[SC_GG] = g_new.g_new,
 // sc[SC_SY + 8*sl + sl] = y.s, sc[SC_SY + 8*slot_i + sl] = s_i.y, sc[SC_SY + 8*sl + slot_i] = s.y_i
 void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,

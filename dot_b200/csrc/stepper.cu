@@ -44,6 +44,9 @@ std::vector<int> balanced_owner(const std::vector<double>& weight, int world) {
 
 Stepper::~Stepper() {
     if (h_sc) cudaFreeHost(h_sc);
+    if (h_sc2) cudaFreeHost(h_sc2);
+    for (auto& e : ev_it)
+        if (e) cudaEventDestroy(e);
     if (h_x) cudaFreeHost(h_x);
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -378,7 +381,7 @@ void Stepper::refresh() {
 
 bool Stepper::precondition_dev(const double* q_dev, double* p_dev, const DotPairs* fuse) {
     const int ndof = 3 * nV;
-    if (chol.n_total > 0) chol.solve(q_dev, gidx.p, xperm.p, st);  // right-hand-side gather fused into the streamed solve
+    if (chol.n_total > 0) chol.solve(q_dev, gidx.p, xperm.p, st, fuse ? fuse->go : nullptr);
     if (cfg.world == 1) {
         if (fuse) {
             launch_scatter_avg_dots(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, *fuse, md_partial.p, counter.p, sc.p, st);
@@ -422,6 +425,7 @@ void Stepper::frame_resident(const int32_t* idx, const double* pos, int count, d
 
 HistList Stepper::hist_list() const {
     HistList H;
+    H.go = nullptr;
     H.n = (int)hist.size();
     for (int i = 0; i < LB_MAXH; ++i) {
         H.slot[i] = 0;
@@ -460,6 +464,163 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
     bool sg_valid = false, stopped = false;
     std::vector<int> free_slots;
     for (int i = 0; i <= cfg.history; ++i) free_slots.push_back(i);
+    // ------------------------------------------------------------------------------------------------------------------------
+    // Speculative iteration pipeline (one GPU, DOT / L-BFGS variants): iteration i+1 is enqueued BEFORE the host has seen the result of
+    // iteration i, under the assumption that holds for almost every iteration - step accepted without halving, new pair kept, not
+    // converged.  The last kernel of iteration i evaluates exactly that predicate on the device and writes a flag; every kernel of
+    // iteration i+1 returns at once if it is 0.  The host then only CONFIRMS iteration i while the GPU already runs i+1: no host round
+    // trip and no launch gaps inside the loop, and the arithmetic (hence every iteration log) is unchanged.  When the assumption fails
+    // (a halving, a rejected pair, convergence - the latter once per time step) the host state is rolled back and the exceptional
+    // case is handled on the synchronous path below.
+    // ------------------------------------------------------------------------------------------------------------------------
+    static const bool spec_env = !(std::getenv("DOTGPU_SPECULATE") && std::getenv("DOTGPU_SPECULATE")[0] == '0');
+    const bool speculate = spec_env && cfg.world == 1 && !newton && cfg.history > 0 && !debug_ls_fail;
+    if (speculate) {
+        if (!h_sc2) {
+            DG_CUDA(cudaMallocHost((void**)&h_sc2, 2 * SC_COUNT * sizeof(double)));
+            DG_CUDA(cudaEventCreateWithFlags(&ev_it[0], cudaEventDisableTiming));
+            DG_CUDA(cudaEventCreateWithFlags(&ev_it[1], cudaEventDisableTiming));
+            spec_flags.alloc(2);
+        }
+        // energy of the accepted point lives on the device too
+        DG_CUDA(cudaMemcpyAsync(sc.p + SC_EPREV, sc.p + SC_E, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        struct HostState {
+            std::deque<int> hist;
+            std::vector<int> free_slots;
+            double *x, *x0, *g, *g_old;
+            bool sg_valid;
+        };
+        auto save = [&]() { return HostState{hist, free_slots, x.p, x0.p, g.p, g_old.p, sg_valid}; };
+        auto restore = [&](const HostState& h) {
+            hist = h.hist; free_slots = h.free_slots; x.p = h.x; x0.p = h.x0; g.p = h.g; g_old.p = h.g_old; sg_valid = h.sg_valid;
+        };
+        int enq = 0;  // iterations enqueued so far in this time step
+        // enqueue one iteration on the current host state; returns the candidate slot of its new pair
+        auto enqueue = [&](const int* go, int* flag_out) -> int {
+            HistList H = hist_list();
+            H.go = go;
+            if (H.n > 0 && !sg_valid) {
+                DotPairs P;
+                P.go = go;
+                P.n = H.n;
+                for (int i = 0; i < H.n; ++i) { P.a[i] = H.S[i]; P.b[i] = g.p; P.out[i] = SC_SG + H.slot[i]; }
+                launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
+            }
+            launch_lbfgs_q(n, q.p, g.p, H, sc.p, st);
+            if (pc_ev.size() < 2 * (size_t)(enq + 1)) {
+                cudaEvent_t a, b;
+                DG_CUDA(cudaEventCreate(&a));
+                DG_CUDA(cudaEventCreate(&b));
+                pc_ev.push_back(a);
+                pc_ev.push_back(b);
+            }
+            DotPairs P;
+            P.go = go;
+            P.n = H.n + 1;
+            for (int i = 0; i < H.n; ++i) { P.a[i] = H.Y[i]; P.b[i] = p.p; P.out[i] = SC_YP + H.slot[i]; }
+            P.a[H.n] = g.p; P.b[H.n] = p.p; P.out[H.n] = SC_P0G;
+            DG_CUDA(cudaEventRecord(pc_ev[2 * enq], st));
+            precondition_dev(q.p, p.p, &P);
+            DG_CUDA(cudaEventRecord(pc_ev[2 * enq + 1], st));
+            launch_lbfgs_p(n, p.p, H, sc.p, st);
+            const double* alpha_dev = unit_step ? nullptr : sc.p + SC_ALPHA;
+            if (!unit_step) launch_quadform_alpha(3 * nV, g_ia.p, g_ja.p, a_all.p, p.p, qf_partial.p, counter.p, sc.p, st, go);
+            std::swap(x.p, x0.p);
+            launch_axpy_dev(n, x.p, x0.p, p.p, alpha_dev, 1.0, st, go);
+            const int sl = free_slots.back();
+            launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, S[sl].p, Y[sl].p, sl, alpha_dev, 1.0, H, md_partial.p, counter.p, sc.p,
+                                 true, st, flag_out, target);
+            DG_CUDA(cudaMemcpyAsync(h_sc2 + (enq & 1) * SC_COUNT, sc.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+            DG_CUDA(cudaEventRecord(ev_it[enq & 1], st));
+            ++enq;
+            return sl;
+        };
+        // the host-side effect of "step accepted, pair kept"
+        auto accept = [&](int sl) {
+            std::swap(g.p, g_old.p);
+            sg_valid = true;
+            free_slots.pop_back();
+            hist.push_back(sl);
+            if ((int)hist.size() > cfg.history) {
+                free_slots.push_back(hist.front());
+                hist.pop_front();
+            }
+        };
+        int pending_sl = enqueue(nullptr, spec_flags.p + 0);  // iteration 0 of the time step: nothing to speculate on
+        ++evals;
+        while (true) {
+            const int cur = enq - 1;               // index of the iteration waiting for confirmation
+            const HostState before = save();       // host state as iteration `cur` left it (pointers already swapped by enqueue)
+            int next_sl = -1;
+            const bool ahead = iters + 1 < cfg.max_iters;
+            if (ahead) {
+                accept(pending_sl);
+                next_sl = enqueue(spec_flags.p + (cur & 1), spec_flags.p + ((cur + 1) & 1));
+            }
+            DG_CUDA(cudaEventSynchronize(ev_it[cur & 1]));
+            const double* hs = h_sc2 + (cur & 1) * SC_COUNT;
+            double alpha = unit_step ? 1.0 : hs[SC_ALPHA], Et = hs[SC_E];
+            if (debug_ls_fail) Et = INFINITY;
+            const bool ok = !debug_ls_fail && (Et <= E) && (hs[SC_YS_NEW] > 0.0) && (hs[SC_GG] > target);
+            if (ok && ahead) {                     // the common case: iteration `cur` is confirmed, cur + 1 is already running
+                E = Et;
+                gg = hs[SC_GG];
+                ++iters;
+                ++evals;
+                iter_log.insert(iter_log.end(), {alpha, E, gg});
+                pending_sl = next_sl;
+                continue;
+            }
+            // ---- exceptional: roll the host back to the state after iteration `cur` was enqueued; whatever was enqueued behind it
+            //      sees flag 0 and does nothing (the device evaluated the same predicate on the same numbers) ----
+            restore(before);
+            DG_CUDA(cudaStreamSynchronize(st));
+            DG_CUDA(cudaGetLastError());
+            std::memcpy(h_sc, hs, SC_COUNT * sizeof(double));
+            const int sl = pending_sl;
+            const HistList H = hist_list();
+            if (Et > E && alpha > 0.0) {  // back-tracking (Optimizer.cpp:803-833)
+                while (true) {
+                    alpha /= 2.0;
+                    ++halvings;
+                    if (alpha == 0.0) {
+                        stopped = true;
+                        break;
+                    }
+                    launch_axpy_dev(n, x.p, x0.p, p.p, nullptr, alpha, st);
+                    Et = energy_at(x.p);
+                    if (debug_ls_fail) Et = INFINITY;
+                    ++evals;
+                    if (!(Et > E)) break;
+                }
+                launch_gradient_pair(mesh, x.p, xt.p, dtsq, g_old.p, p.p, g.p, S[sl].p, Y[sl].p, sl, nullptr, alpha, H, md_partial.p, counter.p,
+                                     sc.p, false, st);
+                fetch_scalars(0, SC_COUNT);
+            }
+            E = Et;
+            std::swap(g.p, g_old.p);
+            gg = h_sc[SC_GG];
+            sg_valid = true;
+            if (h_sc[SC_YS_NEW] > 0.0) {
+                free_slots.pop_back();
+                hist.push_back(sl);
+                if ((int)hist.size() > cfg.history) {
+                    free_slots.push_back(hist.front());
+                    hist.pop_front();
+                }
+            }
+            if (stopped) break;
+            ++iters;
+            iter_log.insert(iter_log.end(), {alpha, E, gg});
+            if (!(gg > target) || iters >= cfg.max_iters) break;
+            // continue from the corrected state: the accepted energy goes back to the device, the next iteration is not speculative
+            h_sc[SC_EPREV] = E;
+            DG_CUDA(cudaMemcpyAsync(sc.p + SC_EPREV, h_sc + SC_EPREV, sizeof(double), cudaMemcpyHostToDevice, st));
+            pending_sl = enqueue(nullptr, spec_flags.p + ((enq) & 1));
+            ++evals;
+        }
+        spec_enq = enq;
+    } else
     do {
         // ---- L-BFGS two-loop with the decomposed Hessian as initialiser (DOTTimeStepper.cpp:384-466), compact form: the inner
         //      products against the history are taken in two multi-dot passes, the recursions run on scalars ----
@@ -467,6 +628,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         const HistList H = hist_list();
         if (H.n > 0 && !sg_valid) {  // normally produced by the previous iteration's fused gradient kernel
             DotPairs P;
+            P.go = nullptr;
             P.n = H.n;
             for (int i = 0; i < H.n; ++i) { P.a[i] = H.S[i]; P.b[i] = g.p; P.out[i] = SC_SG + H.slot[i]; }
             launch_dots(n, P, md_partial.p, counter.p, sc.p, st);
@@ -481,6 +643,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         }
         {
             DotPairs P;  // second multi-dot: y_i . p0 and g . p0, taken inside the scatter pass on one GPU
+            P.go = nullptr;
             P.n = H.n + 1;
             for (int i = 0; i < H.n; ++i) { P.a[i] = H.Y[i]; P.b[i] = p.p; P.out[i] = SC_YP + H.slot[i]; }
             P.a[H.n] = g.p; P.b[H.n] = p.p; P.out[H.n] = SC_P0G;
@@ -587,7 +750,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         stats->ms_solve = b;
         stats->ms_refresh = c;
         double pc = 0.0;
-        for (int i = 0; i < iters; ++i) {
+        for (int i = 0; i < (speculate ? spec_enq : iters); ++i) {
             float t = 0;
             cudaEventElapsedTime(&t, pc_ev[2 * i], pc_ev[2 * i + 1]);
             pc += t;

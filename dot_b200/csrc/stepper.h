@@ -56,6 +56,10 @@ struct Stepper {
     DevBuf<double> sc;               // device scalars
     DevBuf<unsigned> counter;
     double* h_sc = nullptr;          // pinned mirror
+    double* h_sc2 = nullptr;         // two pinned mirrors for the speculative pipeline (iteration parity)
+    cudaEvent_t ev_it[2] = {nullptr, nullptr};
+    DevBuf<int> spec_flags;          // device flags written by the last kernel of an iteration (linalg.h)
+    int spec_enq = 0;
     double* h_x = nullptr;           // pinned staging for positions
     double target = 0.0, target_per_tolsq = 0.0;
     bool newton = false;             // DOTGPU_FLAG_NEWTON
