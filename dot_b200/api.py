@@ -454,6 +454,15 @@ class Stepper:
     def launch_count(self):
         return int(lib().dotgpu_stepper_launch_count(self.h))
 
+    def solve_trace(self):
+        """[ctas, 96, 8] uint64 %globaltimer stamps of the last preconditioner application (needs DOTGPU_SOLVE_TRACE=1)."""
+        lib().dotgpu_stepper_get_solve_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        nw = lib().dotgpu_stepper_get_solve_trace(self.h, None, 0)
+        t = np.zeros(max(nw, 0), dtype=np.uint64)
+        if nw > 0:
+            lib().dotgpu_stepper_get_solve_trace(self.h, _p(t), nw)
+        return t.reshape(-1, 96, 8)
+
     def owned(self):
         """Subdomain ids this rank factors and solves."""
         n = lib().dotgpu_stepper_get_owned(self.h, None)

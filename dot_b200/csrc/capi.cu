@@ -615,6 +615,20 @@ int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out) {
         for (size_t i = 0; i < s->s.owned.size(); ++i) out[i] = s->s.owned[i];
     return (int)s->s.owned.size();
 }
+int dotgpu_stepper_get_solve_trace(dotgpu_stepper* s, uint64_t* out, int64_t max_words) {
+    API_BEGIN
+    DG_REQUIRE(s, "null argument");
+    CholBatch& C = s->s.chol;
+    const int64_t nw = (int64_t)C.d_trace.n;
+    if (out && nw > 0) {
+        DG_REQUIRE(max_words >= nw, "trace buffer too small");
+        DG_CUDA(cudaSetDevice(s->s.cfg.device));
+        DG_CUDA(cudaStreamSynchronize(s->s.st));
+        DG_CUDA(cudaMemcpy(out, C.d_trace.p, (size_t)nw * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    return (int)std::min<int64_t>(nw, 1 << 30);
+    API_END
+}
 int dotgpu_partition_nodes(int nV, int nT, const int32_t* tets, int k, int32_t* npart_out) {
     API_BEGIN
     metis_partition_nodes(nV, nT, tets, k, npart_out);

@@ -75,6 +75,7 @@ struct CholBatch {
     DevBuf<int> d_ptasks;
     DevBuf<double> Pf, Pb, Ubuf;
     DevBuf<unsigned> d_cnt;
+    DevBuf<unsigned long long> d_trace;   // DOTGPU_SOLVE_TRACE=1: per-chunk timestamps of the last solve (experiments)
     int64_t pk_total = 0;
     int n_solve_tasks = 0, n_pack_tasks = 0, stage_dbl = 0, vec_dbl = 0, solve_grid = 0, solve_nstage = 3, solve_dbg = 0;
     size_t solve_smem = 0;

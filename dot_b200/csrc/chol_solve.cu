@@ -50,14 +50,21 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting thread sleeps in hardware until the phase completes (or the hint expires) instead
+// of re-polling - the helper warps (producer, gatherers, signallers) share their SM sub-partitions with the consumer warps, and
+// their polling loops were taking issue slots from the products (chunk trace r2: the consumer warp that shares its sub-partition
+// with the producer took 1.3 us per chunk, the one that does not 0.6 us)
+#ifndef DOTGPU_MBAR_SUSPEND_NS
+#define DOTGPU_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)DOTGPU_MBAR_SUSPEND_NS)
         : "memory");
     return ok != 0;
 }
@@ -76,6 +83,19 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// DOTGPU_SOLVE_TRACE=1 (experiments, tools/k5_trace.py): %globaltimer stamps of the first 96 chunks of every CTA, 6 per chunk
+// {posted, vector ready, data + vector seen by the consumers, products done (after the consumer barrier), published, queue slot,
+// warp 0 out of its products, last consumer warp out of its products}; 8 words per chunk
+constexpr int TRACE_CHUNKS = 96;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DG_TRACE(slot, it_)                                                                                       \
+    do {                                                                                                          \
+        if (trace && (it_) < TRACE_CHUNKS) trace[((size_t)blockIdx.x * TRACE_CHUNKS + (it_)) * 8 + (slot)] = gtime(); \
+    } while (0)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
 __device__ __forceinline__ void gatherer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(GATHERERS) : "memory"); }
 
@@ -95,7 +115,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
     k_solve_stream(int ngroups, const SolveTask* __restrict__ chunks, const int* __restrict__ rows,
                    const int* __restrict__ rel, const double* __restrict__ Pf, const double* __restrict__ Pb, const double* __restrict__ b,
                    const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, unsigned* claim, int stage_dbl,
-                   int vec_dbl, int dbg, const int* __restrict__ go) {
+                   int vec_dbl, int dbg, const int* __restrict__ go, unsigned long long* trace) {
     if (go && *go == 0) return;  // speculatively enqueued iteration whose assumption failed (linalg.h): every CTA leaves at once
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);          // NSTAGE * stage_dbl
@@ -169,6 +189,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
                         mbar_expect_tx(&full[st], bytes);
                         tma_load_1d(ring + (size_t)st * stage_dbl, (s_chunk[st].kind ? Pb : Pf) + s_chunk[st].src, bytes, &full[st]);
                     }
+                    DG_TRACE(0, it);
+                    if (trace && it < TRACE_CHUNKS) trace[((size_t)blockIdx.x * TRACE_CHUNKS + it) * 8 + 5] = g0;
                 }
                 ++it;
             }
@@ -204,6 +226,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
             unsigned* p = cnt + s_chunk[st].sig_idx;
             mbar_arrive(&empty[st]);
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+            if (trace && n * NSTAGE + st < TRACE_CHUNKS) trace[((size_t)blockIdx.x * TRACE_CHUNKS + (n * NSTAGE + st)) * 8 + 4] = gtime();
         }
         return;
     }
@@ -255,6 +278,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
                     const unsigned need = (unsigned)T.dep_need;
                     const unsigned* p = cnt + T.dep_idx;
                     while (ld_acquire(p) < need) {
+                        __nanosleep(40);   // back off: the poll loop shares an SM sub-partition with a consumer warp
                     }
                 }
                 gatherer_sync();
@@ -285,6 +309,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
                 s_vb[st] = vb;
                 s_base[st] = base;
                 mbar_arrive(&vready[st]);
+                DG_TRACE(1, it);
             }
         }
         return;
@@ -299,6 +324,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
         if (!s_live[st]) break;
         mbar_wait(&vready[st], par);
         mbar_wait(&full[st], par);
+        if (tid == 0) DG_TRACE(2, it);
         const SolveTask& T = s_chunk[st];
         const int m = T.m, ns = T.ns, r0 = T.r0, r1 = T.r1, col0 = T.col0;
         const int vbase = s_base[st];
@@ -309,12 +335,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
         // lane group (W = 1: one thread per row, no reduction; W = 32: a warp per row).  Short rows dominate the factor (update rows
         // of leaf-side supernodes), so most chunks run with small W and finish in one pass with a short or no shuffle tree.
         const int nrows = r1 - r0;
-        int W = 32;
-        while (W > 1 && nrows * W > CONSUMERS) W >>= 1;
-        const int sub = tid / W, sl = tid % W, nsub = CONSUMERS / W;
+        // W = 2^lw lanes per row.  Shifts and masks only: a division by the run-time W costs ~200 cycles, and this code runs once per
+        // chunk in every consumer warp (chunk trace r2: ~700 cycles of fixed overhead per chunk, a third of a chunk's time at 1M tets)
+        int lw = 5;
+        while (lw > 0 && (nrows << lw) > CONSUMERS) --lw;
+        const int W = 1 << lw;
+        const int sub = tid >> lw, sl = tid & (W - 1), nsub = CONSUMERS >> lw;
         const bool fwd = T.kind == 0;
         const int tri0 = r0 < ns ? (ns - r0) * (ns + r0 + 1) / 2 : 0;  // forward: entries of the triangle rows r0..ns-1 of this chunk
         const long long pU = T.pU;
+        const long long tl0 = trace ? clock64() : 0;
         if (!(dbg & 1))
         for (int i0 = 0; i0 < nrows; i0 += nsub) {
             const int r = r0 + i0 + sub;
@@ -361,8 +391,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
                 else U[pU + idx[r - vbase]] = vec[r] + sum;
             }
         }
+        if (trace && it < TRACE_CHUNKS && (tid & 31) == 0) {   // per-warp cycles inside the product loop + the chunk's shape
+            const long long dtc = clock64() - tl0;
+            unsigned long long* q = trace + ((size_t)blockIdx.x * TRACE_CHUNKS + it) * 8;
+            if (tid == 0) q[6] = (unsigned long long)dtc | ((unsigned long long)nrows << 32) | ((unsigned long long)W << 48) | ((unsigned long long)T.kind << 56);
+            if (tid == CONSUMERS - 32) q[7] = (unsigned long long)dtc;
+            if (tid == 32) q[4] = (unsigned long long)dtc;   // (slot 4 is overwritten by the signaller later: read it as warp 1 only if published == 0)
+        }
         consumer_sync();  // all results stored, all shared-memory reads of this stage (data, descriptor, vector) done
-        if (tid == 0) mbar_arrive(&done[st]);
+        if (tid == 0) {
+            mbar_arrive(&done[st]);
+            DG_TRACE(3, it);
+        }
     }
 }
 
@@ -601,6 +641,10 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
     Ubuf.alloc(std::max<int64_t>(ub, 1));
     Ubuf.zero(st);
     d_cnt.alloc(3 * (size_t)std::max(nsn, 1) + 2);
+    if (env_int("DOTGPU_SOLVE_TRACE", 0)) {
+        d_trace.alloc((size_t)nsm * 4 * TRACE_CHUNKS * 8);
+        d_trace.zero(st);
+    }
     DG_CUDA(cudaFuncSetAttribute(k_solve_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaFuncSetAttribute(k_solve_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DG_CUDA(cudaFuncSetAttribute(k_solve_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -633,7 +677,7 @@ void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStre
     unsigned* claim = d_cnt.p + 3 * (size_t)std::max(nsuper_total, 1);
 #define DG_SOLVE_LAUNCH(NS)                                                                                                         \
     k_solve_stream<NS><<<solve_grid, SOLVE_THREADS, solve_smem, st>>>(n_solve_tasks, d_stasks.p, d_rows.p, d_rel.p, Pf.p, Pb.p, b, \
-                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg, go)
+                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg, go, d_trace.p)
     if (solve_nstage == 2) DG_SOLVE_LAUNCH(2);
     else if (solve_nstage == 3) DG_SOLVE_LAUNCH(3);
     else DG_SOLVE_LAUNCH(4);

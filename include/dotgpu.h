@@ -259,6 +259,10 @@ int dotgpu_stepper_set_rel_tol(dotgpu_stepper* s, double rel_tol);
  * refreshes (K3+K4+factor) / preconditioner applications (K5) on resident data, return avg ms by CUDA events */
 int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* ms_out);
 int64_t dotgpu_stepper_launch_count(dotgpu_stepper* s); /* kernels launched by this handle so far */
+/* diagnostics (DOTGPU_SOLVE_TRACE=1 at create time): %globaltimer stamps of the first 96 chunks of every CTA of the last preconditioner
+ * application, 8 x uint64 per (CTA, chunk): posted, vector ready, data landed, products done, published, queue slot, warp 0 / last warp out of the products.  Returns the number
+ * of uint64 words (0: tracing off); out may be NULL to query the size. */
+int dotgpu_stepper_get_solve_trace(dotgpu_stepper* s, uint64_t* out, int64_t max_words);
 /* the subdomains this rank factors and solves (ascending; balanced by nnz(L) over the ranks); returns their number */
 int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out);
 int dotgpu_stepper_get_solver_info(dotgpu_stepper* s, int sub, dotgpu_solver_info* info);
