@@ -256,6 +256,7 @@ def gpu_frames(ctx, wl, steps, warmup, profile_mode=False, with_kernels=True, wi
     out["n_sub"] = sum(i.n for i in infos)
     out["flops"] = sum(i.flops for i in infos)
     out["owned_subdomains"] = len(owned)
+    out["fill_stats"] = stp.fill_stats()
     if with_kernels:
         # per-kernel device times on the final state (CUDA events on the stepper's stream)
         names = ["energy", "gradient", "elem_hessians", "fill", "factorize", "precondition", "dot"]
@@ -372,6 +373,19 @@ def main():
             kernels[n].update({"algorithmic_bytes": bytes_per[n], "GB/s": gbs, "frac_hbm": gbs / hbm})
     kernels["elem_hessians"]["note"] = "bytes moved by this layout: 280 B read + 720 B written per tet (10 unique 3x3 blocks); the reference's 12x12 layout would be 1432 B/tet"
     kernels["factorize"].update({"flops": R["flops"], "GFLOP/s": R["flops"] / (kms["factorize"] * 1e-3) / 1e9})
+    # K4: every stored matrix value is written once (8 B), every gathered elemental 3x3 block read once (72 B) + 4 B of gather list
+    nnz_a, nblk, ngat = R["fill_stats"]
+    fill_bytes = 8.0 * nnz_a + 76.0 * ngat
+    kernels["fill"].update({"algorithmic_bytes": fill_bytes, "GB/s": fill_bytes / (kms["fill"] * 1e-3) / 1e9,
+                            "frac_hbm": fill_bytes / (kms["fill"] * 1e-3) / 1e9 / hbm,
+                            "note": "%d stored values written (8 B), %d elemental 3x3 blocks gathered (72 B + 4 B index) into %d matrix blocks" % (nnz_a, ngat, nblk)})
+    # the reference's timer_step activities (main.cpp:867-880) for the GPU side, per time step: in-frame CUDA-event times where the stepper
+    # records them (backSolve = K5 + scatter, the Hessian refresh), the isolated kernel times x their launch counts for the rest
+    its = R["iters"] / max(a.steps, 1)
+    timers_gpu = {"matrixComputation": kms["elem_hessians"], "matrixAssembly": kms["fill"], "symbolicFactorization": 0.0,
+                  "numericalFactorization": kms["factorize"], "backSolve": R["pc_ms"] / max(a.steps, 1),
+                  "lineSearch_eVal+updateHistory": its * kms["gradient"],
+                  "modifyGrad+modifySearchDir+lineSearch_other": max(0.0, R["solve_ms"] / max(a.steps, 1) - R["pc_ms"] / max(a.steps, 1) - its * kms["gradient"])}
 
     # secondary record: config C2 on the reference's own mesh, same code path, short
     secondary = None
@@ -438,7 +452,8 @@ def main():
                                     "hessian+fill": nT / ((kms["elem_hessians"] + kms["fill"]) * 1e-3)},
             "inner_iters": R["iters"], "line_search_halvings": R["halv"], "all_frames_converged": R["conv"], "device_ms_per_step": R["dev_ms"] / a.steps,
             "solve_ms_per_step": R["solve_ms"] / a.steps, "refresh_ms_per_step": R["refresh_ms"] / a.steps, "setup_sec": R["setup_sec"],
-            "nnz_L": R["nnz_l"], "factor_flops": R["flops"], "owned_subdomains_rank0": R["owned_subdomains"]}
+            "nnz_L": R["nnz_l"], "factor_flops": R["flops"], "owned_subdomains_rank0": R["owned_subdomains"],
+            "timers_ms_per_step": timers_gpu}
     if parity is not None:
         line["parity"] = parity
     if secondary is not None:

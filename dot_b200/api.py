@@ -463,6 +463,12 @@ class Stepper:
             lib().dotgpu_stepper_get_solve_trace(self.h, _p(t), nw)
         return t.reshape(-1, 96, 8)
 
+    def fill_stats(self):
+        """(stored matrix values, 3x3 blocks, elemental 3x3 blocks gathered) of this rank's matrix fill."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(lib().dotgpu_stepper_get_fill_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def owned(self):
         """Subdomain ids this rank factors and solves."""
         n = lib().dotgpu_stepper_get_owned(self.h, None)

@@ -79,9 +79,12 @@ void AnimHost::init(int kind_, int nV_, const double* V, double ratio) {
         turn_lo = V[3 * (size_t)turn_v] - (kind == DOTGPU_ANIM_TWISTNSNS ? 1.2 : 0.8);
         turn_hi = V[3 * (size_t)turn_v] + 0.4;
     }
-    if (kind == DOTGPU_ANIM_NULL) fixed_now[0] = 1;  // Mesh::computeFeatures default (Mesh.cpp:593-599)
-    for (auto& h : handles)
-        for (int v : h) fixed_now[v] = 1;
+    if (kind == DOTGPU_ANIM_NULL) {
+        fixed_now[0] = 1;  // Mesh::computeFeatures default (Mesh.cpp:593-599)
+    } else {
+        for (auto& h : handles)
+            for (int v : h) fixed_now[v] = 1;
+    }
 }
 
 void AnimHost::fixed_mask(uint8_t* out) const {

@@ -609,6 +609,21 @@ int dotgpu_stepper_time_kernels(dotgpu_stepper* s, int which, int reps, double* 
     *ms_out = s->s.time_kernels(which, reps);
     API_END
 }
+int dotgpu_stepper_get_fill_stats(dotgpu_stepper* s, int64_t* nnz_out, int64_t* blocks_out, int64_t* gathered_blocks_out) {
+    if (!s) return DOTGPU_ERR_INVALID;
+    const Stepper& S = s->s;
+    int64_t gathered = 0, blocks = 0;
+    auto count = [&](const FillList& f) {
+        blocks += (int64_t)f.ptr.size() - 1;
+        for (int32_t c : f.src) gathered += c >= 0;
+    };
+    count(S.dd.gfill);
+    for (int sd : S.owned) count(S.dd.subs[sd].fill);
+    if (nnz_out) *nnz_out = S.a_off.empty() ? 0 : S.a_off.back();
+    if (blocks_out) *blocks_out = blocks;
+    if (gathered_blocks_out) *gathered_blocks_out = gathered;
+    return DOTGPU_OK;
+}
 int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out) {
     if (!s) return DOTGPU_ERR_INVALID;
     if (out)

@@ -317,13 +317,16 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
                                                       const double* __restrict__ go, double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                       const double* __restrict__ alpha_dev, double alpha_host, HistList H,
                                                       double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    // the multi-GPU twin of k_grad_vertex_pair: the gradient is already reduced over the ranks; forms the new pair and takes every
+    // inner product the next iteration needs: |g|^2, y.s, s.g_new, and per history pair s_h.y, s.y_h, s_h.g_new
+    constexpr int NACC = 3 + 3 * LB_MAXH;
     if (H.go && *H.go == 0) return;
-    __shared__ double shm[8 * (2 + 2 * LB_MAXH)], res[2 + 2 * LB_MAXH];
+    __shared__ double shm[8 * NACC], res[NACC];
     __shared__ bool last;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
-    double acc[2 + 2 * LB_MAXH];
+    double acc[NACC];
 #pragma unroll
-    for (int j = 0; j < 2 + 2 * LB_MAXH; ++j) acc[j] = 0.0;
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
     for (long long i = (long long)blockIdx.x * MD_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * MD_TPB) {
         const double gnew = gn[i];
         const double s = alpha * p[i], y = gnew - go[i];
@@ -333,26 +336,56 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
         }
         acc[0] += gnew * gnew;
         acc[1] += y * s;
+        acc[2] += s * gnew;
 #pragma unroll
         for (int j = 0; j < LB_MAXH; ++j)
             if (j < H.n && Sn) {
-                acc[2 + 2 * j] += H.S[j][i] * y;
-                acc[3 + 2 * j] += s * H.Y[j][i];
+                const double si = H.S[j][i];
+                acc[3 + 3 * j] += si * y;
+                acc[4 + 3 * j] += s * H.Y[j][i];
+                acc[5 + 3 * j] += si * gnew;
             }
     }
-    const int nacc = Sn ? 2 + 2 * H.n : 2;
-    if (!multi_reduce_256<2 + 2 * LB_MAXH>(acc, nacc, shm, res, &last, partial, counter)) return;
+    const int nacc = Sn ? 3 + 3 * H.n : 3;
+    if (!multi_reduce_256<NACC>(acc, nacc, shm, res, &last, partial, counter)) return;
     if ((int)threadIdx.x < nacc) {
         const int j = threadIdx.x;
         const double tot = res[j];
         if (j == 0) sc[SC_GG] = tot;
         else if (j == 1) { sc[SC_YS_NEW] = tot; if (sl >= 0) sc[SC_SY + 8 * sl + sl] = tot; }
+        else if (j == 2) { if (sl >= 0) sc[SC_SG + sl] = tot; }
         else {
-            const int h = (j - 2) >> 1, sh_ = H.slot[h];
-            if ((j & 1) == 0) sc[SC_SY + 8 * sh_ + sl] = tot;  // s_h . y_new
-            else sc[SC_SY + 8 * sl + sh_] = tot;               // s_new . y_h
+            const int h = (j - 3) / 3, kind = (j - 3) % 3, sh_ = H.slot[h];
+            if (kind == 0) sc[SC_SY + 8 * sh_ + sl] = tot;       // s_h . y_new
+            else if (kind == 1) sc[SC_SY + 8 * sl + sh_] = tot;  // s_new . y_h
+            else sc[SC_SG + sh_] = tot;                          // s_h . g_new
         }
     }
+}
+
+// multi-GPU: p holds the all-reduced sum of the subdomain solutions; divide the interface entries by their duplication count
+// (DOTTimeStepper.cpp:447-449) and take the inner products p . P.a[j] in the same pass
+__global__ void __launch_bounds__(MD_TPB) k_divdup_dots(int ndof, const int* __restrict__ dup, double* __restrict__ p, DotPairs P,
+                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+    if (P.go && *P.go == 0) return;
+    __shared__ double shm[8 * 12], res[12];
+    __shared__ bool last;
+    double acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+    for (int d = blockIdx.x * MD_TPB + threadIdx.x; d < ndof; d += gridDim.x * MD_TPB) {
+        double v = p[d];
+        const int du = dup[d / 3];
+        if (du > 1) {
+            v /= (double)du;
+            p[d] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+            if (j < P.n) acc[j] += P.a[j][d] * v;
+    }
+    if (!multi_reduce_256<12>(acc, P.n, shm, res, &last, partial, counter)) return;
+    if ((int)threadIdx.x < P.n) sc[P.out[threadIdx.x]] = res[threadIdx.x];
 }
 
 // p = D^-1 sum of the subdomain copies (DOTTimeStepper.cpp:434-450) and, in the same pass, the inner products of p with the
@@ -436,6 +469,11 @@ void launch_pair_dots(long long n, const double* p, const double* g_new, const d
 void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, const DotPairs& P,
                              double* partial, unsigned* counter, double* sc, cudaStream_t st) {
     k_scatter_dots<<<md_blocks(ndof), MD_TPB, 0, st>>>(ndof, cptr, cidx, xs, dup, p, P, partial, counter, sc);
+    count_launch();
+}
+
+void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
+    k_divdup_dots<<<md_blocks(ndof), MD_TPB, 0, st>>>(ndof, dup, p, P, partial, counter, sc);
     count_launch();
 }
 

@@ -67,7 +67,7 @@ enum ScalarSlot {
     SC_COUNT = 96,
     SC_EPREV = 7   // energy of the last accepted point (speculative iterations compare against it on the device); shares the slot of SC_DOT
 };
-int multidot_partial_count();
+int multidot_partial_count();  // sized for the widest multi-reduction (4 + 3 * LB_MAXH values)
 int multidot_blocks(long long n);  // fixed grid of the deterministic multi-reduction kernels
 // sc[P.out[j]] = a_j . b_j for all pairs in one pass (deterministic: fixed grid, block partials, last block adds them in order)
 void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st);
@@ -90,6 +90,9 @@ void launch_pair_dots(long long n, const double* p, const double* g_new, const d
 // scatter/average of the subdomain solutions fused with the inner products p . P.a[j] -> sc[P.out[j]] (P.b is ignored)
 void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, const DotPairs& P,
                              double* partial, unsigned* counter, double* sc, cudaStream_t st);
+
+// multi-GPU: p = all-reduced sum of the subdomain solutions -> divide by dup and take p . P.a[j] in one pass
+void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st);
 
 // ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
 // p[d] = (sum over the subdomain copies of dof d, in subdomain order) / dup

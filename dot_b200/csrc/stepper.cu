@@ -391,6 +391,10 @@ bool Stepper::precondition_dev(const double* q_dev, double* p_dev, const DotPair
     } else {
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, nullptr, p_dev, st);
         comm->all_reduce_sum(p_dev, ndof, st);
+        if (fuse) {  // division by dup fused with the second multi-dot of the iteration
+            launch_divdup_dots(ndof, dup.p, p_dev, *fuse, md_partial.p, counter.p, sc.p, st);
+            return true;
+        }
         k_div_dup<<<ceil_div(ndof, 256), 256, 0, st>>>(ndof, dup.p, p_dev);
         count_launch();
     }
@@ -705,7 +709,7 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
         E = Et;
         std::swap(g.p, g_old.p);
         gg = h_sc[SC_GG];
-        sg_valid = !multi;  // one GPU: sc[SC_SG + slot] now holds s_i . g for every pair that can be in the next history
+        sg_valid = true;  // sc[SC_SG + slot] now holds s_i . g for every pair that can be in the next history (both paths)
         // ---- history update (DOTTimeStepper.cpp:476-493): keep the pair iff y.s > 0, then drop the oldest beyond `history` ----
         if (sl >= 0 && h_sc[SC_YS_NEW] > 0.0) {
             free_slots.pop_back();

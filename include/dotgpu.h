@@ -263,6 +263,9 @@ int64_t dotgpu_stepper_launch_count(dotgpu_stepper* s); /* kernels launched by t
  * application, 8 x uint64 per (CTA, chunk): posted, vector ready, data landed, products done, published, queue slot, warp 0 / last warp out of the products.  Returns the number
  * of uint64 words (0: tracing off); out may be NULL to query the size. */
 int dotgpu_stepper_get_solve_trace(dotgpu_stepper* s, uint64_t* out, int64_t max_words);
+/* byte model of the matrix fill K4 (bench.py): stored values of [global | owned subdomain] matrices (8 B each, written once per refresh),
+ * 3x3 blocks of those matrices, and elemental 3x3 blocks gathered into them (72 B each, read once per refresh) */
+int dotgpu_stepper_get_fill_stats(dotgpu_stepper* s, int64_t* nnz_out, int64_t* blocks_out, int64_t* gathered_blocks_out);
 /* the subdomains this rank factors and solves (ascending; balanced by nnz(L) over the ranks); returns their number */
 int dotgpu_stepper_get_owned(dotgpu_stepper* s, int32_t* out);
 int dotgpu_stepper_get_solver_info(dotgpu_stepper* s, int sub, dotgpu_solver_info* info);
