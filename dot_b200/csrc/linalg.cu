@@ -1,3 +1,5 @@
+#include <algorithm>
+#include <cstdlib>
 #include "linalg.h"
 #include "reduce.cuh"
 
@@ -200,7 +202,13 @@ void launch_dot(long long n, const double* a, const double* b, double* partial, 
 // ------------------------------------------------------------------------------------------------------------------
 // fused L-BFGS kernels
 constexpr int MD_TPB = 256;
-constexpr int MD_MAX_BLOCKS = 296;  // 2 CTAs per SM
+static int md_max_blocks() {  // grid of the multi-reduction kernels (DOTGPU_MD_BLOCKS: experiments)
+    static const int v = [] {
+        const char* e = std::getenv("DOTGPU_MD_BLOCKS");
+        return e && *e ? std::max(1, std::atoi(e)) : 592;  // 4 CTAs per SM (B200 sweep r2: 296 -> 592 -> 1184: 76.9 -> 76.1 -> 76.7 ms per frame at 1M tets)
+    }();
+    return v;
+}
 
 __global__ void __launch_bounds__(MD_TPB) k_dots(long long n, DotPairs P, double* __restrict__ partial, unsigned* __restrict__ counter,
                                                  double* __restrict__ sc) {
@@ -269,6 +277,9 @@ __global__ void __launch_bounds__(256) k_lbfgs_p(long long n, double* __restrict
     p[e] = v;
 }
 
+// p^T H p with the symmetric matrix stored as CSR-upper: QF_LANES lanes share a row so that the value / column-index reads of a warp
+// are 4 contiguous segments instead of 32 scattered ones (a row holds ~23 entries; one thread per row ran at 0.4 of HBM)
+constexpr int QF_LANES = 8, QF_ROWS = 256 / QF_LANES;
 __global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __restrict__ ia, const int* __restrict__ ja,
                                                         const double* __restrict__ a, const double* __restrict__ p,
                                                         double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
@@ -276,14 +287,24 @@ __global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __rest
     if (go && *go == 0) return;
     __shared__ double sh[8];
     __shared__ bool last;
-    int i = blockIdx.x * 256 + threadIdx.x;
+    const int sl = threadIdx.x & (QF_LANES - 1), grp = threadIdx.x / QF_LANES;
     double s = 0.0;
-    if (i < n) {
-        const double pi = p[i];
-        int b = ia[i], e = ia[i + 1];
+#pragma unroll 2
+    for (int rr = 0; rr < QF_LANES; ++rr) {   // a CTA covers 256 consecutive rows, QF_ROWS at a time
+        const int i = blockIdx.x * 256 + rr * QF_ROWS + grp;
+        int b = 0, e = 0;
+        if (i < n) {
+            b = ia[i];
+            e = ia[i + 1];
+        }
         double off = 0.0;
-        for (int k = b + 1; k < e; ++k) off += a[k] * p[ja[k]];
-        s = pi * (a[b] * pi + 2.0 * off);  // first entry of every row is the diagonal
+        for (int k = b + 1 + sl; k < e; k += QF_LANES) off += a[k] * p[ja[k]];
+#pragma unroll
+        for (int o = QF_LANES / 2; o > 0; o >>= 1) off += __shfl_down_sync(0xffffffffu, off, o, QF_LANES);
+        if (sl == 0 && i < n) {
+            const double pi = p[i];
+            s += pi * (a[b] * pi + 2.0 * off);  // first entry of every row is the diagonal
+        }
     }
     double r = cta_sum256(s, sh);
     if (threadIdx.x == 0) {
@@ -437,8 +458,8 @@ void launch_velocity(int nV, double* vel, const double* x, const double* xn, dou
     long long n = 3LL * nV;
     EW_LAUNCH(k_velocity, n, n, vel, x, xn, dt);
 }
-int multidot_partial_count() { return MD_MAX_BLOCKS * (4 + 3 * LB_MAXH); }
-int multidot_blocks(long long n) { return (int)std::min<long long>(MD_MAX_BLOCKS, std::max<long long>(1, (n + MD_TPB - 1) / MD_TPB)); }
+int multidot_partial_count() { return md_max_blocks() * (4 + 3 * LB_MAXH); }
+int multidot_blocks(long long n) { return (int)std::min<long long>(md_max_blocks(), std::max<long long>(1, (n + MD_TPB - 1) / MD_TPB)); }
 static int md_blocks(long long n) { return multidot_blocks(n); }
 
 void launch_dots(long long n, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st) {

@@ -309,7 +309,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
         b->zero(st);
     }
     xperm.alloc(std::max<int64_t>(chol.n_total, 1));
-    qf_partial.alloc(ceil_div((long long)n3, 256) + 1);
+    qf_partial.alloc(ceil_div((long long)n3, 32) + 1);  // one partial per CTA of k_quadform_alpha (32 rows each)
     dot_partial.alloc(dot_partial_count((long long)n3));
     md_partial.alloc(multidot_partial_count());
     S.resize(cfg.history + 1);
