@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdotgpu.so")
 SOURCES = ["energy_kernels.cu", "chol_numeric.cu", "chol_solve.cu", "linalg.cu", "stepper.cu", "capi.cu", "mesh_host.cpp", "chol_symbolic.cpp",
-           "anim_host.cpp", "comm.cpp", "partition_host.cpp"]
+           "anim_host.cpp", "comm.cpp", "partition_host.cpp", "peer_reduce.cu"]
 METIS_LIB = os.path.join(HERE, "libdotmetis.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O3",
               "-Xptxas", "-v"]

@@ -10,6 +10,7 @@ struct Id128 { char b[128]; };
 typedef int (*fn_get_id)(Id128*);
 typedef int (*fn_init_rank)(void**, int, Id128, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 
@@ -41,6 +42,7 @@ void check(void* lib, int rc, const char* what) {
 }  // namespace
 
 Comm::~Comm() {
+    peer.reset();
     if (comm && lib) {
         fn_destroy d = (fn_destroy)dlsym(lib, "ncclCommDestroy");
         if (d) d(comm);
@@ -65,7 +67,28 @@ void Comm::init(const void* uid, int rank_, int world_) {
     check(lib, sym<fn_init_rank>(lib, "ncclCommInitRank")(&comm, world, id, rank), "ncclCommInitRank");
 }
 
+bool Comm::enable_peer(long long cap_doubles, cudaStream_t st) {
+    std::unique_ptr<PeerReduce> p(new PeerReduce());
+    if (p->init(*this, cap_doubles, st)) peer = std::move(p);
+    return (bool)peer;
+}
+
 void Comm::all_reduce_sum(double* buf, long long n, cudaStream_t st) {
+    if (peer && n <= peer->cap) {
+        peer->push(buf, n, st);
+        peer->wait_sum(buf, n, st);
+        return;
+    }
+    nccl_all_reduce_sum(buf, n, st);
+}
+
+void Comm::all_gather_bytes(const void* send_dev, void* recv_dev, size_t bytes_per_rank, cudaStream_t st) {
+    static fn_allgather ag = nullptr;
+    if (!ag) ag = sym<fn_allgather>(lib, "ncclAllGather");
+    check(lib, ag(send_dev, recv_dev, bytes_per_rank, 0 /* ncclInt8 */, comm, st), "ncclAllGather");
+}
+
+void Comm::nccl_all_reduce_sum(double* buf, long long n, cudaStream_t st) {
     static fn_allreduce ar = nullptr;
     if (!ar) ar = sym<fn_allreduce>(lib, "ncclAllReduce");
     // ncclFloat64 = 8, ncclSum = 0

@@ -4,14 +4,59 @@
 #pragma once
 #include "common.h"
 
+#include <memory>
+
 namespace dotgpu {
+constexpr int PEER_MAX_RANKS = 16;
+struct Comm;
+
+// kernel-side views of one exchange (peer.cuh): where a producer stores this rank's vector / where a consumer finds all of them
+struct PeerDst {
+    double* slot[PEER_MAX_RANKS];    // where MY vector goes in rank r's buffer (this epoch's parity)
+    unsigned* flag[PEER_MAX_RANKS];  // MY flag word in rank r's buffer
+    unsigned* counter;               // CTA counter of the producer kernel (local)
+    int world;
+    unsigned epoch;
+};
+struct PeerSrc {
+    const double* slots;             // [world][cap], this epoch's parity (local memory, written by the peers); world == 0: unused
+    const unsigned* flags;           // [world]
+    long long cap;
+    int world;
+    unsigned epoch;
+};
+
+// One-shot all-reduce over cudaIpc-mapped peer memory (peer_reduce.cu): push = store my vector into every rank's slot + flag,
+// wait_sum = wait for every rank's flag, add the slots in rank order.
+struct PeerReduce {
+    int rank = 0, world = 1;
+    long long cap = 0;                        // doubles per slot
+    void* base = nullptr;                     // own buffer: [flags | CTA counter | 2 parities x world slots x cap]
+    void* peer_base[PEER_MAX_RANKS] = {};     // the same buffer of every rank, mapped here
+    unsigned epoch = 0;
+    bool ok = false;
+    ~PeerReduce();
+    bool init(Comm& c, long long cap_doubles, cudaStream_t st);
+    void push(const double* buf, long long n, cudaStream_t st);
+    void wait_sum(double* out, long long n, cudaStream_t st);
+    // fused use: a producer kernel stores into begin() and ends with peer_publish(); a consumer kernel enqueued after it waits on
+    // src() and adds the slots itself (peer.cuh)
+    PeerDst begin();      // opens the next epoch
+    PeerSrc src() const;  // the current epoch
+};
+
 struct Comm {
     void* lib = nullptr;
     void* comm = nullptr;
     int rank = 0, world = 1;
+    std::unique_ptr<PeerReduce> peer;  // set by enable_peer when every rank could map every other rank's buffer
     ~Comm();
     static void unique_id(void* out128);
     void init(const void* unique_id128, int rank, int world);
+    // vectors of up to cap_doubles go through peer memory from now on (DOTGPU_PEER_REDUCE=0: keep NCCL); returns whether enabled
+    bool enable_peer(long long cap_doubles, cudaStream_t st);
     void all_reduce_sum(double* buf, long long n, cudaStream_t st);
+    void nccl_all_reduce_sum(double* buf, long long n, cudaStream_t st);
+    void all_gather_bytes(const void* send_dev, void* recv_dev, size_t bytes_per_rank, cudaStream_t st);
 };
 }  // namespace dotgpu

@@ -1,6 +1,8 @@
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "linalg.h"
+#include "peer.cuh"
 #include "reduce.cuh"
 
 namespace dotgpu {
@@ -337,11 +339,18 @@ __global__ void k_axpy_dev(long long n, double* __restrict__ out, const double* 
 __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double* __restrict__ p, const double* __restrict__ gn,
                                                       const double* __restrict__ go, double* __restrict__ Sn, double* __restrict__ Yn, int sl,
                                                       const double* __restrict__ alpha_dev, double alpha_host, HistList H,
-                                                      double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
-    // the multi-GPU twin of k_grad_vertex_pair: the gradient is already reduced over the ranks; forms the new pair and takes every
-    // inner product the next iteration needs: |g|^2, y.s, s.g_new, and per history pair s_h.y, s.y_h, s_h.g_new
+                                                      double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
+                                                      PeerSrc src, double* __restrict__ gn_out, int with_energy) {
+    // the multi-GPU twin of k_grad_vertex_pair: forms the new pair and takes every inner product the next iteration needs: |g|^2,
+    // y.s, s.g_new, and per history pair s_h.y, s.y_h, s_h.g_new.  The gradient is either already reduced over the ranks (gn) or
+    // still lies as one slot per rank in peer-written memory (src.world > 0): then this kernel IS the second half of the all-reduce
+    // - it waits for the ranks' flags, adds the slots in rank order, stores the reduced gradient to gn_out and the energy to sc[SC_E]
     constexpr int NACC = 3 + 3 * LB_MAXH;
     if (H.go && *H.go == 0) return;
+    if (src.world > 0) {
+        peer_wait_flags(src);
+        if (with_energy && blockIdx.x == 0 && threadIdx.x == 0) sc[SC_E] = peer_sum(src, n);  // [g ; E]: the energy partials ride at index n
+    }
     __shared__ double shm[8 * NACC], res[NACC];
     __shared__ bool last;
     const double alpha = alpha_dev ? *alpha_dev : alpha_host;
@@ -349,7 +358,13 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
 #pragma unroll
     for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
     for (long long i = (long long)blockIdx.x * MD_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * MD_TPB) {
-        const double gnew = gn[i];
+        double gnew;
+        if (src.world > 0) {
+            gnew = peer_sum(src, i);
+            gn_out[i] = gnew;
+        } else {
+            gnew = gn[i];
+        }
         const double s = alpha * p[i], y = gnew - go[i];
         if (Sn) {
             Sn[i] = s;
@@ -386,21 +401,22 @@ __global__ void __launch_bounds__(MD_TPB) k_pair_dots(long long n, const double*
 
 // multi-GPU: p holds the all-reduced sum of the subdomain solutions; divide the interface entries by their duplication count
 // (DOTTimeStepper.cpp:447-449) and take the inner products p . P.a[j] in the same pass
+// (src.world > 0: the sum is still one slot per rank in peer-written memory - wait for the flags and add the slots in rank order here)
 __global__ void __launch_bounds__(MD_TPB) k_divdup_dots(int ndof, const int* __restrict__ dup, double* __restrict__ p, DotPairs P,
-                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc) {
+                                                        double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
+                                                        PeerSrc src) {
     if (P.go && *P.go == 0) return;
+    if (src.world > 0) peer_wait_flags(src);
     __shared__ double shm[8 * 12], res[12];
     __shared__ bool last;
     double acc[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) acc[j] = 0.0;
     for (int d = blockIdx.x * MD_TPB + threadIdx.x; d < ndof; d += gridDim.x * MD_TPB) {
-        double v = p[d];
+        double v = src.world > 0 ? peer_sum(src, d) : p[d];
         const int du = dup[d / 3];
-        if (du > 1) {
-            v /= (double)du;
-            p[d] = v;
-        }
+        if (du > 1) v /= (double)du;
+        if (du > 1 || src.world > 0) p[d] = v;
 #pragma unroll
         for (int j = 0; j < 12; ++j)
             if (j < P.n) acc[j] += P.a[j][d] * v;
@@ -433,6 +449,18 @@ __global__ void __launch_bounds__(MD_TPB) k_scatter_dots(int ndof, const int* __
     }
     if (!multi_reduce_256<12>(acc, P.n, shm, res, &last, partial, counter)) return;
     if ((int)threadIdx.x < P.n) sc[P.out[threadIdx.x]] = res[threadIdx.x];
+}
+
+// multi-GPU: this rank's sum of its subdomain copies goes straight into its slot in every rank's peer buffer (first half of the
+// all-reduce of the search direction, peer_reduce.cu); the last CTA publishes the epoch
+__global__ void __launch_bounds__(256) k_scatter_push(int ndof, const int* __restrict__ cptr, const int* __restrict__ cidx,
+                                                      const double* __restrict__ xs, PeerDst D) {
+    for (int d = blockIdx.x * 256 + threadIdx.x; d < ndof; d += gridDim.x * 256) {
+        double v = 0.0;
+        for (int k = cptr[d]; k < cptr[d + 1]; ++k) v += xs[cidx[k]];
+        for (int r = 0; r < D.world; ++r) D.slot[r][d] = v;
+    }
+    peer_publish(D);
 }
 
 #define EW_LAUNCH(kernel, n, ...)                                              \
@@ -482,8 +510,12 @@ void launch_axpy_dev(long long n, double* out, const double* x0, const double* p
 }
 void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
                       const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
-                      cudaStream_t st) {
-    k_pair_dots<<<md_blocks(n), MD_TPB, 0, st>>>(n, p, g_new, g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc);
+                      cudaStream_t st, const PeerSrc* src, double* g_new_out, bool with_energy) {
+    PeerSrc S;
+    std::memset(&S, 0, sizeof(S));
+    if (src) S = *src;
+    k_pair_dots<<<md_blocks(n), MD_TPB, 0, st>>>(n, p, g_new, g_old, S_new, Y_new, sl, alpha_dev, alpha_host, H, partial, counter, sc, S,
+                                                 g_new_out, with_energy ? 1 : 0);
     count_launch();
 }
 
@@ -493,8 +525,17 @@ void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const d
     count_launch();
 }
 
-void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st) {
-    k_divdup_dots<<<md_blocks(ndof), MD_TPB, 0, st>>>(ndof, dup, p, P, partial, counter, sc);
+void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st,
+                        const PeerSrc* src) {
+    PeerSrc S;
+    std::memset(&S, 0, sizeof(S));
+    if (src) S = *src;
+    k_divdup_dots<<<md_blocks(ndof), MD_TPB, 0, st>>>(ndof, dup, p, P, partial, counter, sc, S);
+    count_launch();
+}
+
+void launch_scatter_push(int ndof, const int* cptr, const int* cidx, const double* xs, const PeerDst& D, cudaStream_t st) {
+    k_scatter_push<<<std::min(592, ceil_div(ndof, 256)), 256, 0, st>>>(ndof, cptr, cidx, xs, D);
     count_launch();
 }
 

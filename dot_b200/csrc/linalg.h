@@ -1,6 +1,7 @@
 // Matrix fill from elemental Hessians, symmetric SpMV / quadratic form on CSR-upper storage, and the
 // dense-vector kernels of the L-BFGS iteration (all scalars stay on the device).
 #pragma once
+#include "comm.h"
 #include "common.h"
 
 namespace dotgpu {
@@ -85,14 +86,19 @@ void launch_axpy_dev(long long n, double* out, const double* x0, const double* p
 // sc[SC_SY + 8*sl + sl] = y.s, sc[SC_SY + 8*slot_i + sl] = s_i.y, sc[SC_SY + 8*sl + slot_i] = s.y_i
 void launch_pair_dots(long long n, const double* p, const double* g_new, const double* g_old, double* S_new, double* Y_new, int sl,
                       const double* alpha_dev, double alpha_host, const HistList& H, double* partial, unsigned* counter, double* sc,
-                      cudaStream_t st);
+                      cudaStream_t st, const PeerSrc* src = nullptr, double* g_new_out = nullptr, bool with_energy = false);
+// (src != nullptr: g_new is still one slot per rank in peer-written memory; the kernel adds the slots in rank order, writes the
+//  reduced gradient to g_new_out and, with_energy, the reduced energy riding at index n to sc[SC_E])
 
 // scatter/average of the subdomain solutions fused with the inner products p . P.a[j] -> sc[P.out[j]] (P.b is ignored)
 void launch_scatter_avg_dots(int ndof, const int* cptr, const int* cidx, const double* xs, const int* dup, double* p, const DotPairs& P,
                              double* partial, unsigned* counter, double* sc, cudaStream_t st);
 
 // multi-GPU: p = all-reduced sum of the subdomain solutions -> divide by dup and take p . P.a[j] in one pass
-void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st);
+void launch_divdup_dots(int ndof, const int* dup, double* p, const DotPairs& P, double* partial, unsigned* counter, double* sc, cudaStream_t st,
+                        const PeerSrc* src = nullptr);
+// multi-GPU: this rank's sum of its subdomain copies -> its slot in every rank's peer buffer + flag (first half of the all-reduce of p)
+void launch_scatter_push(int ndof, const int* cptr, const int* cidx, const double* xs, const PeerDst& D, cudaStream_t st);
 
 // ---- preconditioner gather / scatter (DOTTimeStepper.cpp:414-450) ----
 // p[d] = (sum over the subdomain copies of dof d, in subdomain order) / dup

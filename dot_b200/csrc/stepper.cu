@@ -327,6 +327,7 @@ void Stepper::create(const dotgpu_stepper_config& c, int nV_, int nT_, const dou
     if (cfg.world > 1) {
         comm.reset(new Comm());
         comm->init(cfg.nccl_unique_id, cfg.rank, cfg.world);
+        comm->enable_peer((long long)n3 + 1, st);  // [g ; E] and p go through NVLink peer memory (peer_reduce.cu) when every rank can map it
     }
     target = compute_target();
     target_per_tolsq = target / (cfg.rel_tol * cfg.rel_tol);  // the geometry / material factor: set_rel_tol only rescales it
@@ -373,6 +374,21 @@ void Stepper::eval_sharded(const double* x_dev, double* G) {
     comm->all_reduce_sum(G, n3 + 1, st);
 }
 
+// first half only: this rank's [g ; E] goes into its slot on every rank; the consumer (k_pair_dots) adds the slots.  Returns false
+// when the peer path is not available (then G holds the reduced vector, as after eval_sharded)
+bool Stepper::eval_sharded_push(const double* x_dev, double* G) {
+    if (!comm->peer) {
+        eval_sharded(x_dev, G);
+        return false;
+    }
+    const long long n3 = 3LL * nV;
+    const double* xtp = cfg.rank == 0 ? xt.p : nullptr;
+    launch_energy(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G + n3, st);
+    launch_gradient(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G, st);
+    comm->peer->push(G, n3 + 1, st);
+    return true;
+}
+
 void Stepper::refresh() {
     launch_elem_hessians(mesh, x.p, cfg.dt * cfg.dt, true, st);
     launch_fill(fill, mesh.He.p, a_all.p, st);
@@ -389,6 +405,14 @@ bool Stepper::precondition_dev(const double* q_dev, double* p_dev, const DotPair
         }
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, dup.p, p_dev, st);
     } else {
+        if (comm->peer && fuse) {
+            // all-reduce over peer memory, both halves fused: the scatter kernel stores this rank's sums into every rank's slots
+            // and publishes the epoch; the multi-dot kernel waits for the flags, adds the slots in rank order, divides by dup
+            launch_scatter_push(ndof, cptr.p, cidx.p, xperm.p, comm->peer->begin(), st);
+            const PeerSrc src = comm->peer->src();
+            launch_divdup_dots(ndof, dup.p, p_dev, *fuse, md_partial.p, counter.p, sc.p, st, &src);
+            return true;
+        }
         launch_scatter_avg(ndof, cptr.p, cidx.p, xperm.p, nullptr, p_dev, st);
         comm->all_reduce_sum(p_dev, ndof, st);
         if (fuse) {  // division by dup fused with the second multi-dot of the iteration
@@ -677,7 +701,12 @@ void Stepper::frame_core(dotgpu_frame_stats* stats, bool copy_back) {
                                      a_dev, a_host, H, md_partial.p, counter.p, sc.p, with_energy, st);
                 return;
             }
-            eval_sharded(x.p, g_old.p);
+            if (eval_sharded_push(x.p, g_old.p)) {  // peer memory: the pair kernel is the second half of the all-reduce
+                const PeerSrc src = comm->peer->src();
+                launch_pair_dots(n, p.p, nullptr, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, a_dev, a_host, H,
+                                 md_partial.p, counter.p, sc.p, st, &src, g_old.p, with_energy);
+                return;
+            }
             if (with_energy) DG_CUDA(cudaMemcpyAsync(sc.p + SC_E, g_old.p + n3, sizeof(double), cudaMemcpyDeviceToDevice, st));
             launch_pair_dots(n, p.p, g_old.p, g.p, sl >= 0 ? S[sl].p : nullptr, sl >= 0 ? Y[sl].p : nullptr, sl, a_dev, a_host, H, md_partial.p,
                              counter.p, sc.p, st);

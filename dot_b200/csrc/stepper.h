@@ -75,6 +75,7 @@ struct Stepper {
     // world > 1: energy and gradient of the incremental potential at x_dev, summed over the ranks: G[0..3nV) = gradient,
     // G[3nV] = energy (one all-reduce of 3nV + 1 doubles; the inertia terms are added by rank 0 only)
     void eval_sharded(const double* x_dev, double* G);
+    bool eval_sharded_push(const double* x_dev, double* G);  // first half of the peer-memory all-reduce only (stepper.cu)
 
     ~Stepper();
     void create(const dotgpu_stepper_config& c, int nV, int nT, const double* V_rest, const int32_t* tets, const int32_t* epart,
