@@ -43,6 +43,10 @@ void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, doubl
 // gradient + new L-BFGS pair + every inner product of the next iteration's first loop in one pass (see k_grad_vertex_pair);
 // with_energy: also sc[SC_E] = incremental potential at x (K1 fused into K2: the line search needs both at the same point)
 struct HistList;
+struct PeerDst;
+// several GPUs: energy + gradient of this rank's tets in one pass, stored as [g ; E] into this rank's slot of every rank's peer
+// buffer (first half of the all-reduce, peer_reduce.cu); xTilde only on the rank that adds the inertia terms
+void launch_gradient_push(DeviceMesh& m, const double* x, const double* xTilde, double coef, const PeerDst& D, cudaStream_t st);
 void launch_gradient_pair(DeviceMesh& m, const double* x, const double* xTilde, double coef, double* g, const double* pdir,
                           const double* g_old, double* S_new, double* Y_new, int sl, const double* alpha_dev, double alpha_host,
                           const HistList& H, double* partial, unsigned* counter, double* sc, bool with_energy, cudaStream_t st,

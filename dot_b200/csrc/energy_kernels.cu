@@ -7,6 +7,7 @@
 
 #include "device_mesh.h"
 #include "linalg.h"
+#include "peer.cuh"
 #include "reduce.cuh"
 #include "elastic.cuh"
 
@@ -205,6 +206,78 @@ __global__ void __launch_bounds__(256) k_grad_vertex(int nV, const int* __restri
     g[3 * (size_t)v] = g0;
     g[3 * (size_t)v + 1] = g1;
     g[3 * (size_t)v + 2] = g2;
+}
+
+// K2 stage 2 on several GPUs: this rank's share of [g ; E] (its own tets; the inertia terms on rank 0, which passes xt) goes straight
+// into its slot in EVERY rank's peer buffer - the first half of the all-reduce (peer_reduce.cu) - and the last CTA adds the energy
+// partials (elastic: one per CTA of k_grad_block, inertia: one per CTA of this kernel; fixed order), stores the energy at index 3 nV
+// of the slots and publishes the epoch.  The consumer (k_pair_dots) adds the slots in rank order.
+__global__ void __launch_bounds__(256) k_grad_vertex_push(int nV, const int* __restrict__ vp_ptr, const int* __restrict__ vp_idx,
+                                                          const double* __restrict__ part, const unsigned char* __restrict__ fixed,
+                                                          const double* __restrict__ x, const double* __restrict__ xt,
+                                                          const double* __restrict__ mass, PeerDst D, const double* __restrict__ epartial,
+                                                          int n_epartial, double coef, double* __restrict__ ipartial) {
+    __shared__ double shm[8];
+    __shared__ bool last;
+    double ein = 0.0;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < nV; v += gridDim.x * 256) {
+        double gv[3] = {0.0, 0.0, 0.0}, dx[3] = {0.0, 0.0, 0.0};
+        double m = 0.0;
+        if (xt) {
+            m = mass[v];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dx[c] = x[3 * (size_t)v + c] - xt[3 * (size_t)v + c];
+            ein += (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) * m / 2.0;  // inertia energy: ALL vertices (Optimizer.cpp:1204-1211)
+        }
+        if (!fixed[v]) {
+            for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
+                const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
+                gv[0] += p[0]; gv[1] += p[1]; gv[2] += p[2];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gv[c] += m * dx[c];
+        }
+        for (int r = 0; r < D.world; ++r) {
+            double* __restrict__ dst = D.slot[r] + 3 * (size_t)v;
+            dst[0] = gv[0]; dst[1] = gv[1]; dst[2] = gv[2];
+        }
+    }
+    // CTA sum of the inertia energy (fixed order), one partial per CTA
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ein += __shfl_down_sync(0xffffffffu, ein, o);
+        if (lane == 0) shm[warp] = ein;
+        __syncthreads();
+        if (threadIdx.x == 0) ipartial[blockIdx.x] = ((shm[0] + shm[1]) + (shm[2] + shm[3])) + ((shm[4] + shm[5]) + (shm[6] + shm[7]));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(D.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double ve = 0.0, vi = 0.0;
+        for (int i = threadIdx.x; i < n_epartial; i += 32) ve += __ldcg(epartial + i);
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) vi += __ldcg(ipartial + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ve += __shfl_down_sync(0xffffffffu, ve, o);
+            vi += __shfl_down_sync(0xffffffffu, vi, o);
+        }
+        if (threadIdx.x == 0) {
+            const double E = coef * ve + vi;
+            for (int r = 0; r < D.world; ++r) D.slot[r][3 * (size_t)nV] = E;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < D.world) {
+        __threadfence_system();
+        st_release_sys(D.flag[threadIdx.x], D.epoch);
+    }
+    if (threadIdx.x == 0) *D.counter = 0u;
 }
 
 // K2 stage 2 fused with the L-BFGS pair update (DOTTimeStepper.cpp:476-493): besides g_new it forms s = alpha p and
@@ -507,6 +580,18 @@ void launch_gradient(DeviceMesh& m, const double* x, const double* xTilde, doubl
     DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
                 m.g_cptr.p, m.g_cidx.p, m.gpart.p, (double*)nullptr, (const int*)nullptr);
     k_grad_vertex<<<ceil_div(m.nV, 256), 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, g);
+    count_launch();
+}
+
+void launch_gradient_push(DeviceMesh& m, const double* x, const double* xTilde, double coef, const PeerDst& D, cudaStream_t st) {
+    const int nb = ceil_div(m.nT, TPB);
+    if (m.epart.n < (size_t)std::max(nb, 1)) m.epart.alloc(std::max(nb, 1));
+    if (nb > 0)
+        DISPATCH_EN(m, k_grad_block, nb, TPB, st, m.nT, (const int4*)m.tets.p, m.DmInv.p, m.vol.p, m.mu.p, m.lam.p, x, coef, m.lv_ptr.p,
+                    m.g_cptr.p, m.g_cidx.p, m.gpart.p, m.epart.p, (const int*)nullptr);
+    const int grid = std::min(ceil_div(m.nV, 256), m.nsm * 4);  // <= n_partial inertia partials
+    k_grad_vertex_push<<<grid, 256, 0, st>>>(m.nV, m.vp_ptr.p, m.vp_idx.p, m.gpart.p, m.fixed.p, x, xTilde, m.mass.p, D, m.epart.p, nb, coef,
+                                             m.partial.p);
     count_launch();
 }
 

@@ -383,9 +383,9 @@ bool Stepper::eval_sharded_push(const double* x_dev, double* G) {
     }
     const long long n3 = 3LL * nV;
     const double* xtp = cfg.rank == 0 ? xt.p : nullptr;
-    launch_energy(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G + n3, st);
-    launch_gradient(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, G, st);
-    comm->peer->push(G, n3 + 1, st);
+    (void)n3;
+    (void)G;
+    launch_gradient_push(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, comm->peer->begin(), st);  // K1 + K2 + push in two launches
     return true;
 }
 
