@@ -159,8 +159,8 @@ def workload_config(name, wl, steps, warmup, world):
     return {"workload": "%s: %s, %d tets / %d nodes, %s, %s, script %s, dt %g, tol 1e-5"
                         % (name, wl["kind"], nT, nV, wl["energy"], method, wl["anim"], wl["dt"]),
             "l2": "inputs larger than L2, no explicit flush: every L-BFGS iteration streams the solve panels of all subdomains (2 x nnz(L) x 8 B "
-                  "= 3.0 GB on bar1M, 0.2 GB on bar17K vs 126 MB of L2) and every frame rewrites ~4 x that in the Hessian refresh; "
-                  "positions / gradients (3 nV doubles) are L2-resident by design",
+                  "= 2.4 GB on bar1M, 0.2 GB on bar17K vs 126 MB of L2; the exact figure is roofline.algorithmic_bytes_per_launch) and every "
+                  "frame rewrites ~4 x that in the Hessian refresh; positions / gradients (3 nV doubles) are L2-resident by design",
             "subdomains": wl["k"], "tets": nT, "nodes": nV, "energy": wl["energy"], "frames_timed": steps, "frames_warmup": warmup,
             "parallelism": "%d GPU(s): subdomains (factor + solves) and tets (energy / gradient / Hessians) sharded by subdomain, balanced by nnz(L); "
                            "search direction and gradient reduced across ranks every L-BFGS iteration" % world}
@@ -373,6 +373,11 @@ def main():
             kernels[n].update({"algorithmic_bytes": bytes_per[n], "GB/s": gbs, "frac_hbm": gbs / hbm})
     kernels["elem_hessians"]["note"] = "bytes moved by this layout: 280 B read + 720 B written per tet (10 unique 3x3 blocks); the reference's 12x12 layout would be 1432 B/tet"
     kernels["factorize"].update({"flops": R["flops"], "GFLOP/s": R["flops"] / (kms["factorize"] * 1e-3) / 1e9})
+    pk = os.path.join(ROOT, "profiles", "r2", "dmma_peak.json")  # tools/dmma_peak.cu on a B200 of this pool: DMMA m8n8k4 = DFMA = 37.1 TFLOP/s
+    if os.path.exists(pk):
+        f64 = json.load(open(pk))["dmma_m8n8k4_f64_tflops"]
+        kernels["factorize"].update({"fp64_peak_TFLOP/s": f64, "frac_fp64_peak": kernels["factorize"]["GFLOP/s"] / 1e3 / f64,
+                                     "peak_source": "measured (tools/dmma_peak.cu, profiles/r2/dmma_peak.json)"})
     # K4: every stored matrix value is written once (8 B), every gathered elemental 3x3 block read once (72 B) + 4 B of gather list
     nnz_a, nblk, ngat = R["fill_stats"]
     fill_bytes = 8.0 * nnz_a + 76.0 * ngat
@@ -436,9 +441,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(a.workload, {}).get("k_solve_dram_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "K5 k_solve_tasks: all per-subdomain supernodal triangular solves of one preconditioner application "
-                                      "(forward + backward) as one persistent TMA-streamed task-graph kernel (+ the fused gather; the scatter/average kernel is "
-                                      "included in the timed span); rank 0's share at N > 1",
+    roof = {"bound": "hbm", "kernel": "K5 k_solve_stream: all per-subdomain supernodal triangular solves of one preconditioner application "
+                                      "(forward + backward) as one persistent TMA-streamed dataflow kernel (the right-hand-side gather and the "
+                                      "scatter/average [+ exchange at N > 1] kernels are included in the timed span); rank 0's share at N > 1",
             "achieved": k5_gbs, "peak": hbm, "unit": "GB/s", "frac": k5_gbs / hbm, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": k5_bytes, "avg_launch_ms_in_timed_region": k5_ms, "launches_in_timed_region": R["pc_calls"],
             "share_of_frame": R["pc_ms"] / max(R["dev_ms"], 1e-9), "isolated_ms": kms["precondition"]}
