@@ -237,10 +237,8 @@ __global__ void __launch_bounds__(256) k_grad_vertex_push(int nV, const int* __r
 #pragma unroll
             for (int c = 0; c < 3; ++c) gv[c] += m * dx[c];
         }
-        for (int r = 0; r < D.world; ++r) {
-            double* __restrict__ dst = D.slot[r] + 3 * (size_t)v;
-            dst[0] = gv[0]; dst[1] = gv[1]; dst[2] = gv[2];
-        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) peer_store(D, 3 * (long long)v + c, gv[c]);
     }
     // CTA sum of the inertia energy (fixed order), one partial per CTA
     {
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(256) k_grad_vertex_push(int nV, const int* __r
         }
         if (threadIdx.x == 0) {
             const double E = coef * ve + vi;
-            for (int r = 0; r < D.world; ++r) D.slot[r][3 * (size_t)nV] = E;
+            peer_store(D, 3 * (long long)nV, E);
             __threadfence_system();
         }
     }

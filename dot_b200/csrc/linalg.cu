@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) k_scatter_push(int ndof, const int* __res
     for (int d = blockIdx.x * 256 + threadIdx.x; d < ndof; d += gridDim.x * 256) {
         double v = 0.0;
         for (int k = cptr[d]; k < cptr[d + 1]; ++k) v += xs[cidx[k]];
-        for (int r = 0; r < D.world; ++r) D.slot[r][d] = v;
+        peer_store(D, d, v);
     }
     peer_publish(D);
 }

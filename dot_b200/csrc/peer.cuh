@@ -28,8 +28,17 @@ __device__ __forceinline__ void peer_wait_flags(const PeerSrc& S) {
 // sum over the ranks in rank order (bit-identical on every rank); peers wrote these lines: never through this SM's L1
 __device__ __forceinline__ double peer_sum(const PeerSrc& S, long long i) {
     double s = __ldcg(S.slots + i);
-    for (int r = 1; r < S.world; ++r) s += __ldcg(S.slots + (long long)r * S.cap + i);
+    for (int r = 1; r < S.nsum; ++r) s += __ldcg(S.slots + (long long)r * S.cap + i);
     return s;
+}
+// a producer's store of entry i of this rank's vector
+__device__ __forceinline__ void peer_store(const PeerDst& D, long long i, double v) {
+    if (D.slice) {
+        const int s = (int)(i / D.slice);
+        D.slot[s][i - (long long)s * D.slice] = v;
+    } else {
+        for (int r = 0; r < D.world; ++r) D.slot[r][i] = v;
+    }
 }
 // last step of a producer kernel: every CTA calls it with all threads AFTER its stores into the peers' slots
 __device__ __forceinline__ void peer_publish(const PeerDst& D) {

@@ -19,13 +19,37 @@ namespace dotgpu {
 namespace {
 
 constexpr int PR_TPB = 256;
-constexpr size_t PR_HEADER = 256;  // bytes in front of the slots: flags[world] (one per source rank), then the CTA counter
+// bytes in front of the data: round-1 flags[world] at 0 (one per source rank), round-2 flags[world] at 64, CTA counters at 128 / 132
+constexpr size_t PR_HEADER = 256;
 
 __global__ void __launch_bounds__(PR_TPB) k_peer_push(long long n, const double* __restrict__ buf, PeerDst D) {
     for (long long i = (long long)blockIdx.x * PR_TPB + threadIdx.x; i < n; i += (long long)gridDim.x * PR_TPB) {
-        const double v = buf[i];
-        for (int r = 0; r < D.world; ++r) D.slot[r][i] = v;
+        peer_store(D, i, buf[i]);
     }
+    peer_publish(D);
+}
+
+// two-shot, on the owner of a slice: wait for every rank's contribution, add them in rank order, store the sums into every rank's
+// result vector, publish round 2
+__global__ void __launch_bounds__(PR_TPB) k_peer_reduce_bcast(long long nslice, const double* stage, long long slice, int world,
+                                                              const unsigned* flags1, unsigned epoch, PeerBcast B) {
+    {
+        PeerSrc W;
+        W.flags = flags1;
+        W.world = world;
+        W.epoch = epoch;
+        peer_wait_flags(W);
+    }
+    for (long long j = (long long)blockIdx.x * PR_TPB + threadIdx.x; j < nslice; j += (long long)gridDim.x * PR_TPB) {
+        double s = __ldcg(stage + j);
+        for (int r = 1; r < world; ++r) s += __ldcg(stage + (long long)r * slice + j);
+        for (int r = 0; r < world; ++r) B.res[r][j] = s;
+    }
+    PeerDst D;  // only the fields peer_publish reads
+    for (int r = 0; r < world; ++r) D.flag[r] = B.flag2[r];
+    D.counter = B.counter;
+    D.world = world;
+    D.epoch = epoch;
     peer_publish(D);
 }
 
@@ -48,8 +72,18 @@ bool PeerReduce::init(Comm& c, long long cap_doubles, cudaStream_t st) {
     if (world < 2 || world > PEER_MAX_RANKS) return false;
     if (const char* e = std::getenv("DOTGPU_PEER_REDUCE"))
         if (e[0] == '0') return false;
-    cap = (cap_doubles + 15) / 16 * 16;
-    const size_t bytes = PR_HEADER + 2 * (size_t)world * cap * sizeof(double);
+    // two-shot above 4 ranks (DOTGPU_PEER_TWO_SHOT=0/1 overrides): see comm.h
+    bool two = world > 4;
+    if (const char* e = std::getenv("DOTGPU_PEER_TWO_SHOT")) two = e[0] == '1';
+    if (two) {
+        slice = ((cap_doubles + world - 1) / world + 15) / 16 * 16;
+        cap = slice * world;
+    } else {
+        slice = 0;
+        cap = (cap_doubles + 15) / 16 * 16;
+    }
+    // one-shot: 2 parities x world slots x cap; two-shot: 2 parities x (world stages x slice + result vector of cap) = the same size
+    const size_t bytes = PR_HEADER + (two ? 4 : 2 * (size_t)world) * cap * sizeof(double);
     DG_CUDA(cudaMalloc(&base, bytes));
     DG_CUDA(cudaMemsetAsync(base, 0, bytes, st));
     // exchange the IPC handles through the communicator that already exists
@@ -96,19 +130,51 @@ PeerDst PeerReduce::begin() {
     }
     for (int r = 0; r < world; ++r) {
         char* b = static_cast<char*>(peer_base[r]);
-        D.slot[r] = reinterpret_cast<double*>(b + PR_HEADER) + (par * world + rank) * cap;
+        double* data = reinterpret_cast<double*>(b + PR_HEADER);
+        // two-shot data layout per parity: [world stages x slice | result vector of cap]  (2 * cap doubles)
+        D.slot[r] = slice ? data + par * 2 * cap + (size_t)rank * slice : data + (par * world + rank) * cap;
         D.flag[r] = reinterpret_cast<unsigned*>(b) + rank;
     }
     D.counter = reinterpret_cast<unsigned*>(static_cast<char*>(base) + 128);
+    D.slice = slice;
     D.world = world;
     D.epoch = epoch;
     return D;
 }
 
+void PeerReduce::after_push(cudaStream_t st) {
+    if (!slice) return;
+    const size_t par = epoch & 1u;
+    PeerBcast B;
+    for (int r = 0; r < PEER_MAX_RANKS; ++r) {
+        B.res[r] = nullptr;
+        B.flag2[r] = nullptr;
+    }
+    for (int r = 0; r < world; ++r) {
+        char* b = static_cast<char*>(peer_base[r]);
+        B.res[r] = reinterpret_cast<double*>(b + PR_HEADER) + par * 2 * cap + cap + (size_t)rank * slice;
+        B.flag2[r] = reinterpret_cast<unsigned*>(b + 64) + rank;
+    }
+    B.counter = reinterpret_cast<unsigned*>(static_cast<char*>(base) + 132);
+    const double* stage = reinterpret_cast<const double*>(static_cast<const char*>(base) + PR_HEADER) + par * 2 * cap;
+    const int grid = (int)std::min<long long>(296, std::max<long long>(1, (slice + PR_TPB - 1) / PR_TPB));
+    k_peer_reduce_bcast<<<grid, PR_TPB, 0, st>>>(slice, stage, slice, world, reinterpret_cast<const unsigned*>(base), epoch, B);
+    count_launch();
+}
+
 PeerSrc PeerReduce::src() const {
     PeerSrc S;
-    S.slots = reinterpret_cast<const double*>(static_cast<const char*>(base) + PR_HEADER) + (size_t)(epoch & 1u) * world * cap;
-    S.flags = reinterpret_cast<const unsigned*>(base);
+    const double* data = reinterpret_cast<const double*>(static_cast<const char*>(base) + PR_HEADER);
+    const size_t par = epoch & 1u;
+    if (slice) {
+        S.slots = data + par * 2 * cap + cap;   // the result vector the slice owners wrote
+        S.flags = reinterpret_cast<const unsigned*>(static_cast<const char*>(base) + 64);
+        S.nsum = 1;
+    } else {
+        S.slots = data + par * world * cap;
+        S.flags = reinterpret_cast<const unsigned*>(base);
+        S.nsum = world;
+    }
     S.cap = cap;
     S.world = world;
     S.epoch = epoch;
@@ -121,6 +187,7 @@ void PeerReduce::push(const double* buf, long long n, cudaStream_t st) {
     const int grid = (int)std::min<long long>(592, std::max<long long>(1, (n + PR_TPB - 1) / PR_TPB));
     k_peer_push<<<grid, PR_TPB, 0, st>>>(n, buf, D);
     count_launch();
+    after_push(st);
 }
 
 void PeerReduce::wait_sum(double* out, long long n, cudaStream_t st) {

@@ -386,6 +386,7 @@ bool Stepper::eval_sharded_push(const double* x_dev, double* G) {
     (void)n3;
     (void)G;
     launch_gradient_push(mesh_own, x_dev, xtp, cfg.dt * cfg.dt, comm->peer->begin(), st);  // K1 + K2 + push in two launches
+    comm->peer->after_push(st);
     return true;
 }
 
@@ -409,6 +410,7 @@ bool Stepper::precondition_dev(const double* q_dev, double* p_dev, const DotPair
             // all-reduce over peer memory, both halves fused: the scatter kernel stores this rank's sums into every rank's slots
             // and publishes the epoch; the multi-dot kernel waits for the flags, adds the slots in rank order, divides by dup
             launch_scatter_push(ndof, cptr.p, cidx.p, xperm.p, comm->peer->begin(), st);
+            comm->peer->after_push(st);
             const PeerSrc src = comm->peer->src();
             launch_divdup_dots(ndof, dup.p, p_dev, *fuse, md_partial.p, counter.p, sc.p, st, &src);
             return true;
