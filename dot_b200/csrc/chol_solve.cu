@@ -9,13 +9,14 @@
 // bandwidth benchmark with a dependency graph on top:
 //   * panels are stored PACKED and in BOTH orientations (Pf: rows of S_s, triangle packed; Pb: columns of S_s =
 //     rows of S_s^T, triangle packed), so that every task (a range of rows) is one contiguous byte range;
-//   * a producer warp claims tasks from a global queue (topological order: forward levels up, then backward levels
-//     down) and streams their byte ranges into a shared-memory ring with 1-D bulk TMA copies (cp.async.bulk +
+//   * a producer warp walks its CTA's share of the chunk queue (topological order: forward levels up, then backward levels
+//     down) and streams the byte ranges into a shared-memory ring with 1-D bulk TMA copies (cp.async.bulk +
 //     mbarrier complete_tx).  The factor is read-only during a solve, so the stream runs AHEAD of the dependency
 //     chain: when a supernode's inputs become ready its panel rows are already in shared memory;
-//   * 8 consumer warps wait for the data (mbarrier) and for the task's dependencies (per-supernode completion
-//     counters, acquire loads), gather the right-hand side / update vector, do the row.vector products out of shared
-//     memory and publish the results (release);
+//   * 4 gatherer warps wait for the chunk's dependency (per-supernode completion counters, acquire loads) and build the
+//     right-hand side / update vector of the supernode in shared memory, one supernode ahead of the consumers;
+//   * 4 consumer warps wait for the data and the vector (mbarriers), do the row.vector products out of shared memory and
+//     store the results; a signaller lane per ring stage publishes the chunk (release reduction on the waiting counter);
 //   * the queue slots are dealt to the CTAs round-robin (CTA c: slots c, c+G, ...), so the chunks of one tree level run on
 //     different CTAs at the same time and every dependency of a slot sits earlier in some resident CTA's list:
 //     no deadlock for any number of resident CTAs (several solver handles may run concurrently).
@@ -31,7 +32,7 @@ namespace dotgpu {
 
 namespace {
 
-constexpr int SOLVE_GROUP_MAX = 4;  // chunks claimed together (they share one gather of the supernode's vector); queue slots are padded to it
+constexpr int SOLVE_GROUP_MAX = 4;  // chunks per queue slot (they share one gather of the supernode's vector); slots are padded to it
 constexpr int CONSUMERS = 128;   // 4 warps: row . vector products
 #ifndef DOTGPU_GATHERERS
 #define DOTGPU_GATHERERS 128
@@ -100,21 +101,21 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ void gatherer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(GATHERERS) : "memory"); }
 
 // counters: [0,nsn) forward chunks done per supernode, [nsn,2nsn) backward chunks done, [2nsn,3nsn) children whose forward
-// phase is complete, [3nsn] the queue head
+// phase is complete
 //
-// Warp roles (CTA = 8 consumer warps + producer warp + gatherer warp):
-//   producer  (31 lanes)  claims queue slots, posts chunk descriptors, issues the TMA copies           -> posted[st], full[st]
+// Warp roles (CTA = 4 consumer warps + producer warp + 4 gatherer warps + signaller warp):
+//   producer  (31 lanes)  walks the CTA's queue slots, posts chunk descriptors, issues the TMA copies  -> posted[st], full[st]
 //   signaller (1 lane)    publishes finished chunks: fence + completion counters                       <- done[st] -> empty[st]
-//   gatherer  (32 lanes)  per chunk: waits for the chunk's dependency and builds the supernode's vector
+//   gatherers (128)       per chunk: waits for the chunk's dependency and builds the supernode's vector
 //                         (right-hand side + children updates / ancestors' solution) in shared memory  <- posted[st] -> vready[st]
-//   consumers (256)       row . vector products out of shared memory, results to global memory         <- full, vready -> done[st]
+//   consumers (128)       row . vector products out of shared memory, results to global memory         <- full, vready -> done[st]
 // The global-memory latencies (queue, descriptors, dependency polls, gathers, fences) all sit in the helper warps and overlap the
 // consumers' work on earlier chunks.
 template <int NSTAGE>
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
     k_solve_stream(int ngroups, const SolveTask* __restrict__ chunks, const int* __restrict__ rows,
                    const int* __restrict__ rel, const double* __restrict__ Pf, const double* __restrict__ Pb, const double* __restrict__ b,
-                   const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, unsigned* claim, int stage_dbl,
+                   const int* __restrict__ gidx, double* y, double* U, double* x, unsigned* cnt, int stage_dbl,
                    int vec_dbl, int dbg, const int* __restrict__ go, unsigned long long* trace) {
     if (go && *go == 0) return;  // speculatively enqueued iteration whose assumption failed (linalg.h): every CTA leaves at once
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -140,9 +141,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_THREADS <= 256 ? 4 : 3)
     __syncthreads();
 
     if (tid >= CONSUMERS && tid < CONSUMERS + 31) {
-        // ------------------------------ producer (31 lanes): claim groups, stream their chunks ------------------------------
-        // Everything the producer needs from global memory is requested one group ahead: the queue claim (atomic) and the
-        // group's chunk descriptors (cp.async into a double buffer), so the TMA issue rate is not bound by load latency.
+        // ------------------------------ producer (31 lanes): stream the chunks of this CTA's queue slots ------------------------------
+        // The chunk descriptors of a slot are requested one slot ahead (cp.async into a double buffer), so the TMA issue rate is
+        // not bound by load latency.
         constexpr unsigned PM = 0x7fffffffu;
         const int lane = tid - CONSUMERS;
         auto fetch = [&](int buf, unsigned g) {
@@ -486,8 +487,8 @@ void CholBatch::build_solve_plan(const std::vector<SNDesc>& sn, cudaStream_t st)
             }
     }
     pk_total = pf;
-    // ---- chunks (one TMA copy each) and groups (claimed as a unit; the vector of a supernode is gathered once per group) ----
-    // tuning knobs (defaults measured on B200): stage size in doubles, ring depth, chunks per claimed group
+    // ---- chunks (one TMA copy each) and queue slots of <= SOLVE_GROUP_MAX chunks (the vector of a supernode is gathered once per slot) ----
+    // tuning knobs (defaults measured on B200): stage size in doubles, ring depth, chunks per slot
     auto env_int = [](const char* name, int dflt) {
         const char* v = std::getenv(name);
         return v && *v ? std::atoi(v) : dflt;
@@ -674,10 +675,9 @@ void CholBatch::solve(const double* b, const int* gidx, double* x_perm, cudaStre
         gidx = nullptr;
     }
     DG_CUDA(cudaMemsetAsync(d_cnt.p, 0, d_cnt.bytes(), st));
-    unsigned* claim = d_cnt.p + 3 * (size_t)std::max(nsuper_total, 1);
 #define DG_SOLVE_LAUNCH(NS)                                                                                                         \
     k_solve_stream<NS><<<solve_grid, SOLVE_THREADS, solve_smem, st>>>(n_solve_tasks, d_stasks.p, d_rows.p, d_rel.p, Pf.p, Pb.p, b, \
-                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, claim, stage_dbl, vec_dbl, solve_dbg, go, d_trace.p)
+                                                                       gidx, ywork.p, Ubuf.p, x_perm, d_cnt.p, stage_dbl, vec_dbl, solve_dbg, go, d_trace.p)
     if (solve_nstage == 2) DG_SOLVE_LAUNCH(2);
     else if (solve_nstage == 3) DG_SOLVE_LAUNCH(3);
     else DG_SOLVE_LAUNCH(4);

@@ -1,6 +1,9 @@
-// NCCL all-reduce over NVLink for the one exchange step of the path: the sum of the subdomains'
-// search-direction contributions (DOTTimeStepper.cpp:434-450 is a serial shared-memory loop in the
-// reference).  libnccl is loaded at run time (dlopen) so that single-GPU use has no NCCL dependency.
+// The exchange steps of the path on several GPUs: per L-BFGS iteration the sum over the ranks of [g ; E] and of the subdomains'
+// search-direction contributions (DOTTimeStepper.cpp:434-450 is a serial shared-memory loop in the reference).
+//   Comm        NCCL communicator (libnccl is dlopen()ed, so single-GPU use has no NCCL dependency): bootstrap, fallback
+//               all-reduce, exchange of the IPC handles;
+//   PeerReduce  the same sums over cudaIpc-mapped NVLink peer memory, split into a push half and a wait+sum half that producer
+//               and consumer kernels fuse into their own passes (peer_reduce.cu, peer.cuh).
 #pragma once
 #include "common.h"
 

@@ -638,12 +638,19 @@ def _run_ref_final(exe, tmp, script, frames, tol, threads=None, extra=()):
     return st, np.load(fv)
 
 
+# the three forms of the per-iteration exchange (csrc/peer_reduce.cu): one-shot over peer memory (default up to 4 ranks), two-shot
+# (default above 4 ranks, forced here on 2), and the ncclAllReduce fallback
+_EXCHANGES = {"peer_one_shot": {}, "peer_two_shot": {"DOTGPU_PEER_TWO_SHOT": "1"}, "nccl": {"DOTGPU_PEER_REDUCE": "0"}}
+
+
+@pytest.mark.parametrize("exchange", sorted(_EXCHANGES))
 @pytest.mark.parametrize("name,frames", [("small_snh_k4_twist", 4), ("small_fcr_k3_tsns_dt200", 3)])
-def test_two_ranks_match_one_rank(tmp_path, name, frames):
-    """SURVEY 8(e) on hardware: 2 ranks (one per GPU, NCCL) - subdomains (factor + solves) and tets (energy / gradient) sharded,
-    [g ; E] and the search direction all-reduced every iteration - against the same run on 1 rank, both at tol 1e-9: positions
-    to 1e-7 of the bounding box (the reduction order of g differs between N = 1 and N = 2, so paths agree to rounding, not bitwise),
-    every rank ends with identical positions.  The second case goes through the line-search halving branch on 2 ranks.  Needs 2 GPUs."""
+def test_two_ranks_match_one_rank(tmp_path, name, frames, exchange):
+    """SURVEY 8(e) on hardware: 2 ranks (one per GPU) - subdomains (factor + solves) and tets (energy / gradient) sharded,
+    [g ; E] and the search direction exchanged every iteration (NVLink peer memory, fused into the kernels; or NCCL) - against the
+    same run on 1 rank, both at tol 1e-9: positions to 1e-7 of the bounding box (the reduction order of g differs between N = 1 and
+    N = 2, so paths agree to rounding, not bitwise), every rank ends with identical positions.  The second case goes through the
+    line-search halving branch on 2 ranks.  Needs 2 GPUs."""
     import os
     import subprocess
     import sys
@@ -669,7 +676,7 @@ def test_two_ranks_match_one_rank(tmp_path, name, frames):
     s.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(here, "multi_gpu_worker.py"), name, str(frames), "1e-9", out],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, **_EXCHANGES[exchange]))
     assert r.returncode == 0, r.stderr[-3000:]
     z0, z1 = np.load(out + ".rank0.npz"), np.load(out + ".rank1.npz")
     assert np.array_equal(z0["x"], z1["x"])                       # replicas stay bit-identical across the ranks
