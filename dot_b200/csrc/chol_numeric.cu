@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128) k_trsm(const Task2* __restrict__ tasks, i
         load_chunk(sA, A + k0, d.ns, nrows, w - k0);
         load_chunk(sB, B + k0, NB, w, w - k0);
         __syncthreads();
-        mma_chunk(acc, sA, sB, wr, wc, lane);
+        if (wr * 32 < nrows && wc * 32 < w) mma_chunk(acc, sA, sB, wr, wc, lane);  // warps whose 32x32 block is all padding skip the DMMAs
     }
     __syncthreads();  // all reads of A done before anybody overwrites it
     const int g = lane >> 2, q = lane & 3;
@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks,
     const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns + c0;
     const double* __restrict__ B = L + d.panel + (long long)q0 * d.ns + c0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    // warps whose 32x32 block is all padding, lies strictly above the diagonal, or right of the panel columns skip the DMMAs
+    const bool warp_active = wr * 32 < nrows && wc * 32 < ncols && r0 + wr * 32 + 31 >= q0 + wc * 32 && q0 + wc * 32 < d.ns;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(128) k_update(const Task3* __restrict__ tasks,
         load_chunk(sA, A + k0, d.ns, nrows, w - k0);
         load_chunk(sB, B + k0, d.ns, ncols, w - k0);
         __syncthreads();
-        mma_chunk(acc, sA, sB, wr, wc, lane);
+        if (warp_active) mma_chunk(acc, sA, sB, wr, wc, lane);
     }
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
@@ -381,6 +383,9 @@ __global__ void __launch_bounds__(128) k_update_cb(const Task3* __restrict__ tas
     const double* __restrict__ A = L + d.panel + (long long)r0 * d.ns;
     const double* __restrict__ B = L + d.panel + (long long)q0 * d.ns;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp >> 1, wc = warp & 1;
+    // warps whose 32x32 block is all padding or lies strictly above the diagonal skip the DMMAs (leaf-side fronts have contribution
+    // blocks of ~90 rows: 6 of the 12 warp blocks of their 3 tiles hold anything that is stored)
+    const bool warp_active = wr * 32 < nrows && wc * 32 < ncols && r0 + wr * 32 + 31 >= q0 + wc * 32;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(128) k_update_cb(const Task3* __restrict__ tas
         load_chunk(sA, A + k0, d.ns, nrows, d.ns - k0);
         load_chunk(sB, B + k0, d.ns, ncols, d.ns - k0);
         __syncthreads();
-        mma_chunk(acc, sA, sB, wr, wc, lane);
+        if (warp_active) mma_chunk(acc, sA, sB, wr, wc, lane);
     }
     const int g = lane >> 2, q = lane & 3;
     const int nb = d.m - d.ns;

@@ -184,6 +184,29 @@ __global__ void __launch_bounds__(TPB) k_grad_block(int nT, const int4* __restri
 
 // K2, stage 2: per vertex, add the CTA partials (ascending CTA = ascending tet order), the inertia term m (x - xTilde)
 // (Optimizer.cpp:1239-1252), zero the Dirichlet vertices (Energy.cpp:561).
+// sum of a vertex's per-CTA gradient partials, in list (= ascending CTA = ascending tet) order.  Four list entries at a time: the
+// indices are fetched first, then the 12 values, so that a vertex costs two dependent memory latencies per four partials instead of
+// eight (the stage-2 kernels are latency-bound: ~5 partials per vertex, one thread per vertex)
+__device__ __forceinline__ void gather_partials(const double* __restrict__ part, const int* __restrict__ vp_idx, int b, int e, double (&gv)[3]) {
+    for (int i = b; i < e; i += 4) {
+        int id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) id[u] = i + u < e ? vp_idx[i + u] : -1;
+        double q[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (id[u] >= 0) {
+                const double* __restrict__ p = part + 3 * (size_t)id[u];
+                q[u][0] = p[0]; q[u][1] = p[1]; q[u][2] = p[2];
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (id[u] >= 0) {
+                gv[0] += q[u][0]; gv[1] += q[u][1]; gv[2] += q[u][2];
+            }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_grad_vertex(int nV, const int* __restrict__ vp_ptr, const int* __restrict__ vp_idx,
                                                      const double* __restrict__ part, const unsigned char* __restrict__ fixed,
                                                      const double* __restrict__ x, const double* __restrict__ xt,
@@ -192,10 +215,9 @@ __global__ void __launch_bounds__(256) k_grad_vertex(int nV, const int* __restri
     if (v >= nV) return;
     double g0 = 0.0, g1 = 0.0, g2 = 0.0;
     if (!fixed[v]) {
-        for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
-            const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
-            g0 += p[0]; g1 += p[1]; g2 += p[2];
-        }
+        double gs[3] = {0.0, 0.0, 0.0};
+        gather_partials(part, vp_idx, vp_ptr[v], vp_ptr[v + 1], gs);
+        g0 = gs[0]; g1 = gs[1]; g2 = gs[2];
         if (xt) {
             const double m = mass[v];
             g0 += m * (x[3 * (size_t)v] - xt[3 * (size_t)v]);
@@ -230,10 +252,7 @@ __global__ void __launch_bounds__(256) k_grad_vertex_push(int nV, const int* __r
             ein += (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) * m / 2.0;  // inertia energy: ALL vertices (Optimizer.cpp:1204-1211)
         }
         if (!fixed[v]) {
-            for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
-                const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
-                gv[0] += p[0]; gv[1] += p[1]; gv[2] += p[2];
-            }
+            gather_partials(part, vp_idx, vp_ptr[v], vp_ptr[v + 1], gv);
 #pragma unroll
             for (int c = 0; c < 3; ++c) gv[c] += m * dx[c];
         }
@@ -311,10 +330,7 @@ __global__ void __launch_bounds__(256) k_grad_vertex_pair(int nV, const int* __r
         for (int c = 0; c < 3; ++c) dx[c] = x[3 * (size_t)v + c] - xt[3 * (size_t)v + c];
         acc[3] += (dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) * m / 2.0;  // inertia energy: ALL vertices (Optimizer.cpp:1204-1211)
         if (!fixed[v]) {
-            for (int i = vp_ptr[v]; i < vp_ptr[v + 1]; ++i) {
-                const double* __restrict__ p = part + 3 * (size_t)vp_idx[i];
-                gv[0] += p[0]; gv[1] += p[1]; gv[2] += p[2];
-            }
+            gather_partials(part, vp_idx, vp_ptr[v], vp_ptr[v + 1], gv);
 #pragma unroll
             for (int c = 0; c < 3; ++c) gv[c] += m * dx[c];
         }

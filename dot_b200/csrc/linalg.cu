@@ -285,15 +285,15 @@ constexpr int QF_LANES = 8, QF_ROWS = 256 / QF_LANES;
 __global__ void __launch_bounds__(256) k_quadform_alpha(int n, const int* __restrict__ ia, const int* __restrict__ ja,
                                                         const double* __restrict__ a, const double* __restrict__ p,
                                                         double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ sc,
-                                                        const int* __restrict__ go) {
+                                                        const int* __restrict__ go, int npass) {
     if (go && *go == 0) return;
     __shared__ double sh[8];
     __shared__ bool last;
     const int sl = threadIdx.x & (QF_LANES - 1), grp = threadIdx.x / QF_LANES;
     double s = 0.0;
 #pragma unroll 2
-    for (int rr = 0; rr < QF_LANES; ++rr) {   // a CTA covers 256 consecutive rows, QF_ROWS at a time
-        const int i = blockIdx.x * 256 + rr * QF_ROWS + grp;
+    for (int rr = 0; rr < npass; ++rr) {   // a CTA covers npass * QF_ROWS consecutive rows, QF_ROWS at a time
+        const int i = (blockIdx.x * npass + rr) * QF_ROWS + grp;
         int b = 0, e = 0;
         if (i < n) {
             b = ia[i];
@@ -501,7 +501,9 @@ void launch_lbfgs_q(long long n, double* q, const double* g, const HistList& H, 
 void launch_lbfgs_p(long long n, double* p, const HistList& H, double* sc, cudaStream_t st) { EW_LAUNCH(k_lbfgs_p, n, n, p, H, sc); }
 void launch_quadform_alpha(int n, const int* ia, const int* ja, const double* a, const double* p, double* partial, unsigned* counter,
                            double* sc, cudaStream_t st, const int* go) {
-    k_quadform_alpha<<<ceil_div(n, 256), 256, 0, st>>>(n, ia, ja, a, p, partial, counter, sc, go);
+    // big matrices: 8 passes per CTA (few partials for the last CTA to add); small ones are latency-bound: one pass, more CTAs
+    const int npass = n >= (1 << 18) ? QF_LANES : 1;
+    k_quadform_alpha<<<ceil_div(n, npass * QF_ROWS), 256, 0, st>>>(n, ia, ja, a, p, partial, counter, sc, go, npass);
     count_launch();
 }
 void launch_axpy_dev(long long n, double* out, const double* x0, const double* p, const double* alpha_dev, double alpha_host,
