@@ -79,7 +79,10 @@ constexpr int EA_COLS = 128, EA_SPLIT_M = 512, EA_FEW_PARENTS = 96;
 __host__ __device__ inline int ea_col_width(int m, int split_m) { return m > split_m ? EA_COLS : m; }
 __global__ void __launch_bounds__(256) k_extend_add(const Task3* __restrict__ tasks, const SNDesc* __restrict__ sn,
                                                     const int* __restrict__ rel, const int* __restrict__ child,
-                                                    double* __restrict__ L, double* __restrict__ CB, int split_m) {
+                                                    double* __restrict__ L, double* __restrict__ CB, int split_m, int phase) {
+    // phase 0: the targets inside the parent's PANEL (columns < ns), before the parent's pivot chain; phase 1: the targets inside
+    // the parent's contribution block, AFTER k_update_cb has stored -L_below L_below^T there.  The contribution blocks therefore
+    // need no zero-fill and k_update_cb no read (one memset + one read pass over all contribution blocks per factorisation less).
     const Task3 tk = tasks[blockIdx.x];
     const SNDesc p = sn[tk.s];
     const int lo = tk.a * 64, hi = min(lo + 64, p.m);
@@ -87,19 +90,21 @@ __global__ void __launch_bounds__(256) k_extend_add(const Task3* __restrict__ ta
     const int clo = tk.b * cw, chi = min(clo + cw, p.m);
     const int nbp = p.m - p.ns;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int s_rng[4];
+    __shared__ int s_rng[5];
     for (int ci = p.child_begin; ci < p.child_end; ++ci) {
         const SNDesc c = sn[child[ci]];
         const int nbc = c.m - c.ns;
         const int* __restrict__ crel = rel + c.rows + c.ns;  // [nbc], ascending
-        if (threadIdx.x < 4) {  // first index with crel[i] >= {lo, hi, clo, chi}
-            const int key = threadIdx.x == 0 ? lo : (threadIdx.x == 1 ? hi : (threadIdx.x == 2 ? clo : chi));
+        if (threadIdx.x < 5) {  // first index with crel[i] >= {lo, hi, clo, chi, ns}
+            const int key = threadIdx.x == 0 ? lo : (threadIdx.x == 1 ? hi : (threadIdx.x == 2 ? clo : (threadIdx.x == 3 ? chi : p.ns)));
             int a = 0, b = nbc;
             while (a < b) { int mid = (a + b) >> 1; if (crel[mid] < key) a = mid + 1; else b = mid; }
             s_rng[threadIdx.x] = a;
         }
         __syncthreads();
-        const int i0 = s_rng[0], i1 = s_rng[1], j0 = s_rng[2], j1 = s_rng[3];
+        const int i0 = s_rng[0], i1 = s_rng[1], js = s_rng[4];
+        // columns of the child's block are ascending in the parent's numbering: [.., js) land in the panel, [js, ..) in the CB
+        const int j0 = phase == 0 ? s_rng[2] : max(s_rng[2], js), j1 = phase == 0 ? min(s_rng[3], js) : s_rng[3];
         const double* __restrict__ ccb = CB + c.cb;
         for (int i = i0 + warp; i < i1; i += 8) {
             const int r = crel[i];
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(128) k_update_cb(const Task3* __restrict__ tas
                 int rr = wr * 32 + i * 8 + g, cc = wc * 32 + j * 8 + 2 * q + e;
                 if (rr < nrows && cc < ncols) {
                     int r = r0 + rr, c = q0 + cc;
-                    if (r >= c) CB[d.cb + (long long)(r - d.ns) * nb + (c - d.ns)] -= acc[i][j][e];
+                    if (r >= c) CB[d.cb + (long long)(r - d.ns) * nb + (c - d.ns)] = -acc[i][j][e];  // the children's blocks are added afterwards
                 }
             }
 }
@@ -871,7 +876,6 @@ void CholBatch::enqueue_factorize(const double* a_all, cudaStream_t st) {
     }
     static const int potrf_dbg = std::getenv("DOTGPU_POTRF_DBG") ? std::atoi(std::getenv("DOTGPU_POTRF_DBG")) : 0;  // experiments only
     DG_CUDA(cudaMemsetAsync(L.p, 0, L.bytes(), st));
-    DG_CUDA(cudaMemsetAsync(CB.p, 0, CB.bytes(), st));
     DG_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), st));
     if (nnz_a_total > 0) {
         k_scatter_a<<<ceil_div(nnz_a_total, 256), 256, 0, st>>>(nnz_a_total, d_amap.p, a_all, L.p);
@@ -883,7 +887,7 @@ void CholBatch::enqueue_factorize(const double* a_all, cudaStream_t st) {
         const LevelPlan& P = plan[lv];
         if (P.extend.cnt) {
             k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task3*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p,
-                                                          P.extend_split_m);
+                                                          P.extend_split_m, 0);
             count_launch();
             mark("extend_add");
         }
@@ -931,6 +935,12 @@ void CholBatch::enqueue_factorize(const double* a_all, cudaStream_t st) {
             k_update_cb<<<P.update_cb.cnt, 128, 0, st>>>((const Task3*)(T + P.update_cb.off), d_sn.p, L.p, CB.p);
             count_launch();
             mark("update_cb");
+        }
+        if (P.extend.cnt && P.update_cb.cnt) {  // the children's contribution blocks into this level's contribution blocks
+            k_extend_add<<<P.extend.cnt, 256, 0, st>>>((const Task3*)(T + P.extend.off), d_sn.p, d_rel.p, d_child.p, L.p, CB.p,
+                                                          P.extend_split_m, 1);
+            count_launch();
+            mark("extend_add_cb");
         }
     }
     DG_CUDA(cudaEventRecord(ev_join, st2));
