@@ -90,6 +90,7 @@ def main(argv=None):
     t0 = time.time()
     cur_tol = s.rel_tol(0)
     dxe = np.zeros_like(x)
+    t_step = {"numericalFactorization": 0.0, "backSolve": 0.0, "lineSearch_eVal": 0.0}
     for f in range(frame0, frame0 + nframes):
         if s.rel_tol(f) != cur_tol:          # Optimizer::setRelGL2Tol only when the script changes it (recomputes targetGRes)
             cur_tol = s.rel_tol(f)
@@ -101,6 +102,11 @@ def main(argv=None):
         fs = stp.frame(x)
         dxe = x - xt_prev
         iters += fs.iters
+        # device times of this time step under the reference's timer_step names (the Hessian refresh = matrix computation +
+        # assembly + numeric factorisation is one CUDA-event span; everything of the iteration besides the solves goes to eVal)
+        t_step["numericalFactorization"] += fs.ms_refresh * 1e-3
+        t_step["backSolve"] += fs.ms_precond * 1e-3
+        t_step["lineSearch_eVal"] += max(0.0, fs.ms_solve - fs.ms_precond) * 1e-3
         stats.frame(f, stp.iter_log())
         if not fs.converged:
             print("frame %d did not converge (|g|^2 = %g > %g)" % (f, fs.grad_sqnorm, fs.target), file=sys.stderr)
@@ -115,6 +121,7 @@ def main(argv=None):
     info = {"frames": nframes, "inner_iters": iters, "fps": nframes / wall if wall > 0 else None, "setup_sec": setup, "nT": int(T.shape[0]),
             "nV": int(V.shape[0]), "parts": int(k), "energy": s.energy, "timeStepper": s.time_stepper, "sumV": float(xs.sum()),
             "sqnormV": float((xs ** 2).sum())}
+    io.write_info_txt(os.path.join(a.out, "info.txt"), V.shape[0], T.shape[0], frame0 + nframes, iters, wall, t_step)  # main.cpp:338-358
     with open(os.path.join(a.out, "info.json"), "w") as f:
         json.dump(info, f)
     print(json.dumps(info))

@@ -258,6 +258,36 @@ class IterStatsWriter:
         self.f.close()
 
 
+# the reference's per-activity timers (main.cpp:867-890): timer ("descent"), timer_step (14 activities), timer_temp3 (7 ADMM activities)
+TIMER_STEP_NAMES = ["matrixComputation", "matrixAssembly", "symbolicFactorization", "numericalFactorization", "backSolve", "lineSearch_other",
+                    "modifyGrad", "modifySearchDir", "updateHistory", "lineSearch_eVal", "fullyImplicit_eComp", "solve_extraComp", "compGrad", "CCD"]
+TIMER_TEMP3_NAMES = ["init", "initPrimal", "initDual", "initWeights", "initCons", "subdSolve", "consSolve"]
+
+
+def _timer_block(names, secs) -> str:
+    """Timer::print (Utils/Timer.hpp:58-69): '<n> activities:', one right-aligned width-10 '%g' value + ' s: <name>' per activity, the total."""
+    out = ["%d activities:" % len(names)]
+    out += ["%10s s: %s" % ("%g" % float(t), n) for n, t in zip(names, secs)]
+    out.append("%10s s: Total" % ("%g" % float(sum(secs))))
+    return "\n".join(out) + "\n"
+
+
+def write_info_txt(path: str, n_verts: int, n_tets: int, iter_num: int, inner_iters: int, descent_sec: float, step_sec: dict | None = None) -> None:
+    """`info.txt` as main.cpp::saveInfoForPresent writes it (main.cpp:338-358): sizes, outer / inner iteration counts, the three timers,
+    a trailing '0 0'.  step_sec maps names of TIMER_STEP_NAMES to seconds (missing: 0); the ADMM timer block is all zeros here."""
+    step_sec = step_sec or {}
+    unknown = set(step_sec) - set(TIMER_STEP_NAMES)
+    if unknown:
+        raise ValueError("not a timer_step activity: %s" % sorted(unknown))
+    with open(path, "w") as f:
+        f.write("%d %d\n" % (n_verts, n_tets))
+        f.write("%d %d 0 0 0\n" % (iter_num, inner_iters))                      # 1.0 - energyParams[0] = 0
+        f.write(_timer_block(["descent"], [descent_sec]))
+        f.write(_timer_block(TIMER_STEP_NAMES, [step_sec.get(n, 0.0) for n in TIMER_STEP_NAMES]))
+        f.write(_timer_block(TIMER_TEMP3_NAMES, [0.0] * len(TIMER_TEMP3_NAMES)))
+        f.write("0 0\n")
+
+
 def write_label_obj(path: str, surface_tris: np.ndarray, tri_to_tet: np.ndarray, epart: np.ndarray) -> None:
     """One `v <label> 0 0` line per surface triangle, label = subdomain of the tet the triangle belongs to."""
     with open(path, "w") as f:

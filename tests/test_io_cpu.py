@@ -156,3 +156,23 @@ def test_script_defaults_are_the_reference_defaults(tmp_path):
     p.write_text("energy FCR\n")
     s = io.parse_script(str(p))
     assert (s.rho, s.YM, s.PR, s.dt, s.duration, s.warm_start, s.handle_ratio) == (1.0, 100.0, 0.4, 0.025, 10.0, 2, 0.01)   # Config.cpp:33-37
+
+
+def test_info_txt_has_the_layout_of_saveInfoForPresent(tmp_path):
+    """info.txt (main.cpp:338-358): '<nV> <nT>', '<iterNum> <innerIterAmt> 0 0 0', Timer::print of the descent timer, of the 14
+    timer_step activities (main.cpp:867-880, same names, same order) and of the 7 ADMM activities, then '0 0'.  Timer::print
+    (Utils/Timer.hpp:58-69): '<n> activities:' + per activity a width-10 right-aligned default-formatted double, ' s: <name>', + Total."""
+    p = tmp_path / "info.txt"
+    io.write_info_txt(str(p), 17315, 86058, 200, 3613, 1.4321, {"numericalFactorization": 0.516, "backSolve": 0.495, "lineSearch_eVal": 0.367})
+    L = p.read_text().splitlines()
+    assert L[0] == "17315 86058" and L[1] == "200 3613 0 0 0"
+    assert L[2] == "1 activities:" and L[3] == "    1.4321 s: descent" and L[4] == "    1.4321 s: Total"
+    assert L[5] == "14 activities:"
+    names = [l.split(" s: ")[1] for l in L[6:20]]
+    assert names == ["matrixComputation", "matrixAssembly", "symbolicFactorization", "numericalFactorization", "backSolve", "lineSearch_other",
+                     "modifyGrad", "modifySearchDir", "updateHistory", "lineSearch_eVal", "fullyImplicit_eComp", "solve_extraComp", "compGrad", "CCD"]
+    assert L[9] == "     0.516 s: numericalFactorization" and L[6] == "         0 s: matrixComputation"
+    assert L[20] == "     1.378 s: Total"
+    assert L[21] == "7 activities:" and L[29] == "         0 s: Total" and L[30] == "0 0" and len(L) == 31
+    with pytest.raises(ValueError):
+        io.write_info_txt(str(p), 1, 1, 1, 1, 0.0, {"notATimer": 1.0})
